@@ -1,0 +1,288 @@
+/*
+ * wva_b200.h — C-ABI of the B200-native Analyze -> Optimize hot path of the
+ * Workload-Variant-Autoscaler (llm-d-incubation/inferno-autoscaler).
+ *
+ * The reference is pure Go (CGO_ENABLED=0, Dockerfile:25) and has no FFI for this
+ * path.  This header is the boundary a cgo shim binds (see INTEGRATION.md and go/):
+ * every entry point names the reference Go function(s) it replaces, file:line
+ * relative to the reference tree.
+ *
+ * Conventions
+ *   - plain C99 POD, no callbacks, no retained caller pointers: every call copies
+ *     what it needs before returning (cgo pointer rules).
+ *   - return 0 (WVA_OK) or a negative WVA_E* code; never aborts, never prints.
+ *     wva_last_error(ctx) gives a human readable message for the last failure.
+ *   - one in-flight call per ctx (the reference path is non re-entrant too: it goes
+ *     through package globals core.TheSystem / analyzer.Model, pkg/core/system.go:12,
+ *     pkg/analyzer/utils.go:73).
+ *   - strings (accelerator, type, model, class, server names) are interned to dense
+ *     indices by the host side; the native side sees integers only.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels
+ *     and fails with WVA_ECUDA when no device is usable.
+ *
+ * Arithmetic contract: float32/float64 typing, operation order and rounding points
+ * are those of the reference (pkg/analyzer, pkg/core/allocation.go); results are
+ * bit-identical to the Go implementation for finite inputs.
+ */
+#ifndef WVA_B200_H
+#define WVA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WVA_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define WVA_OK          0
+#define WVA_EINVAL     -1   /* bad argument / inconsistent sizes                    */
+#define WVA_ECUDA      -2   /* CUDA runtime failure (no device, OOM, launch error) */
+#define WVA_ESTATE     -3   /* call order violated (e.g. solve before analyze)     */
+#define WVA_ENOSOLUTION -4  /* "no feasible allocations found" (internal/optimizer/optimizer.go:38-40) */
+#define WVA_ENONFINITE -5   /* a candidate value is NaN: ordering of the greedy solver is undefined  */
+
+/* ---- tunables (package vars of the reference; part of the parity contract) */
+#define WVA_MAX_QUEUE_TO_BATCH_RATIO 10      /* pkg/config/defaults.go:18 */
+#define WVA_ACCEL_PENALTY_FACTOR     0.1f    /* pkg/config/defaults.go:21 */
+#define WVA_EPSILON                  0.001f  /* pkg/analyzer/queueanalyzer.go:8  */
+#define WVA_STABILITY_SAFETY         0.1f    /* pkg/analyzer/queueanalyzer.go:11 */
+#define WVA_BISECT_TOL               1e-6f   /* pkg/analyzer/utils.go:8 */
+#define WVA_BISECT_MAXIT             100     /* pkg/analyzer/utils.go:9 */
+#define WVA_DEFAULT_PRIORITY         100     /* pkg/config/defaults.go:27-33 */
+
+/* ---- saturation policies: pkg/config/config.go:4-41 ---------------------- */
+#define WVA_POLICY_NONE                 0
+#define WVA_POLICY_PRIORITY_EXHAUSTIVE  1
+#define WVA_POLICY_PRIORITY_ROUND_ROBIN 2
+#define WVA_POLICY_ROUND_ROBIN          3
+
+/* ---- special accelerator indices ---------------------------------------- */
+#define WVA_ACC_NONE    (-1)  /* the empty accelerator name ""                     */
+#define WVA_ACC_UNKNOWN (-2)  /* a non-empty name that is not in the accelerator map */
+
+/*
+ * System image, structure of arrays (host pointers; the library copies).
+ * Source of truth for the fields: pkg/config/types.go:29-37 (AcceleratorSpec),
+ * :64-84 (ModelAcceleratorPerfData), :92-104 (ServiceClassSpec/ModelTarget),
+ * :112-139 (ServerSpec/AllocationData/ServerLoadSpec), :52-61 (capacity).
+ * The per-server SLO/priority arrays are the (class, model) lookups of
+ * pkg/core/allocation.go:64-70 and pkg/core/server.go:92-97 resolved by the host.
+ */
+typedef struct wva_system_soa {
+    int32_t n_servers;   /* S */
+    int32_t n_accels;    /* A */
+    int32_t n_models;    /* M */
+    int32_t n_types;     /* T */
+
+    /* accelerators [A] */
+    const float*   acc_cost;          /* AcceleratorSpec.Cost                       */
+    const int32_t* acc_multiplicity;  /* AcceleratorSpec.Multiplicity               */
+    const int32_t* acc_type;          /* dense index of AcceleratorSpec.Type, [0,T) */
+
+    /* accelerator types [T] */
+    const int64_t* type_capacity;     /* System.capacity[type]; a type absent from the map is 0 */
+
+    /* model x accelerator perf table [M*A], row-major by model */
+    const float*   perf_alpha;        /* DecodeParms.Alpha   */
+    const float*   perf_beta;         /* DecodeParms.Beta    */
+    const float*   perf_gamma;        /* PrefillParms.Gamma  */
+    const float*   perf_delta;        /* PrefillParms.Delta  */
+    const int32_t* perf_max_batch;    /* MaxBatchSize        */
+    const int32_t* perf_at_tokens;    /* AtTokens            */
+    const int32_t* perf_acc_count;    /* AccCount (<=0 means 1, pkg/core/model.go:45-54) */
+    const uint8_t* perf_valid;        /* model.PerfData(acc) != nil */
+
+    /* servers [S] */
+    const int32_t* srv_model;         /* dense model index, -1 = model not in system  */
+    const float*   srv_arrival_rpm;   /* ServerLoadSpec.ArrivalRate (req/min)         */
+    const int32_t* srv_in_tokens;     /* AvgInTokens                                  */
+    const int32_t* srv_out_tokens;    /* AvgOutTokens                                 */
+    const float*   srv_slo_ttft;      /* Target.TTFT                                  */
+    const float*   srv_slo_itl;       /* Target.ITL                                   */
+    const float*   srv_slo_tps;       /* Target.TPS                                   */
+    const uint8_t* srv_target_valid;  /* service class exists AND has a target for the model */
+    const int32_t* srv_priority;      /* Server.Priority(): class priority or 100     */
+    const int32_t* srv_min_replicas;  /* ServerSpec.MinNumReplicas                    */
+    const int32_t* srv_max_batch;     /* ServerSpec.MaxBatchSize override, 0 = none   */
+    const uint8_t* srv_keep_acc;      /* ServerSpec.KeepAccelerator                   */
+    const int32_t* srv_cur_acc;       /* CurrentAlloc.Accelerator: index, WVA_ACC_NONE, WVA_ACC_UNKNOWN */
+    const int32_t* srv_cur_replicas;  /* CurrentAlloc.NumReplicas                     */
+    const float*   srv_cur_cost;      /* CurrentAlloc.Cost                            */
+} wva_system_soa;
+
+/*
+ * Allocation records, structure of arrays (caller-allocated, length n).
+ * Mirrors core.Allocation (pkg/core/allocation.go:13-24).
+ */
+typedef struct wva_alloc_soa {
+    int32_t* acc;           /* Allocation.accelerator as index; WVA_ACC_NONE for the zero-replica zero-load record */
+    int64_t* num_replicas;  /* Go int */
+    int64_t* batch_size;    /* Go int */
+    float*   cost;
+    float*   value;
+    float*   itl;
+    float*   ttft;
+    float*   rho;
+    float*   max_arrv_rate_per_replica;  /* req/msec */
+} wva_alloc_soa;
+
+/* analyzer.AnalysisMetrics, pkg/analyzer/queueanalyzer.go:61-71 (same field order) */
+typedef struct wva_metrics {
+    float throughput;       /* req/sec */
+    float avg_resp_time;    /* msec */
+    float avg_wait_time;    /* msec */
+    float avg_num_in_serv;
+    float avg_prefill_time; /* msec */
+    float avg_token_time;   /* msec */
+    float max_rate;         /* req/sec */
+    float rho;
+} wva_metrics;
+
+/* candidate status byte of the grid sweep */
+#define WVA_CAND_OK          0  /* Analyze succeeded                                            */
+#define WVA_CAND_FEASIBLE    1  /* bit 0 set: Analyze succeeded AND all SLO/replica constraints hold */
+#define WVA_CAND_ERR_PAIR    2  /* pair lookups fail (allocation.go:41-70) or not a candidate accelerator (server.go:70-82) */
+#define WVA_CAND_ERR_CONFIG  4  /* NewQueueAnalyzer rejects (queueanalyzer.go:337-352)          */
+#define WVA_CAND_ERR_RATE_LE0 6 /* Analyze: rate <= 0 (queueanalyzer.go:135-137)                */
+#define WVA_CAND_ERR_RATE_MAX 8 /* Analyze: rate > RateRange.Max (:140-143)                     */
+#define WVA_CAND_ERR_MODEL   10 /* Analyze: model invalid (:147-150)                            */
+
+/* per-server winner of the grid sweep */
+typedef struct wva_grid_best {
+    int32_t acc;        /* accelerator index, -1 when no candidate is feasible */
+    int32_t replicas;
+    int32_t batch;
+    float   cost;       /* acc.Cost * float32(numInstances * replicas)         */
+    float   value;      /* TransitionPenalty(current -> candidate)             */
+    float   itl;
+    float   ttft;
+    float   rho;
+} wva_grid_best;
+
+typedef struct wva_optimizer_spec {   /* pkg/config/types.go:151-155 */
+    int32_t unlimited;
+    int32_t delayed_best_effort;
+    int32_t saturation_policy;        /* WVA_POLICY_*; SaturatedAllocationPolicyEnum(string) done by host */
+} wva_optimizer_spec;
+
+typedef struct wva_ctx wva_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+
+/* Create a context bound to one CUDA device (one process per GPU).  The only slow
+ * call (CUDA context creation); the Go side makes it once per process. */
+int  wva_ctx_create(int device, wva_ctx** out);
+void wva_ctx_destroy(wva_ctx* ctx);
+const char* wva_last_error(const wva_ctx* ctx);   /* ctx may be NULL: returns the create error */
+int  wva_abi_version(void);
+
+/* Replaces core.NewSystem + System.SetFromSpec (pkg/core/system.go:67-90) and the
+ * manager.NewManager side effect core.TheSystem = system (pkg/manager/manager.go:13-19).
+ * Uploads the image to HBM; invalidates previous analysis. */
+int wva_system_upload(wva_ctx* ctx, const wva_system_soa* host);
+
+/* Multi-GPU sharding: this rank owns servers [first, first+count) of the
+ * uploaded image; analysis kernels touch only those; solve/allocate_by_type produce the
+ * rank's partial results.  Default shard = everything. */
+int wva_set_shard(wva_ctx* ctx, int32_t first_server, int32_t count);
+
+/* ---- Analyze ------------------------------------------------------------- */
+
+/* Replaces Server.Calculate for all servers (pkg/core/server.go:55-67), i.e. one
+ * core.CreateAllocation (pkg/core/allocation.go:27-163) per (server, accelerator)
+ * followed by value = curAllocation.TransitionPenalty(alloc) (:291-300).
+ * out has S*A records (server-major); feasible[s*A+a] = 1 when CreateAllocation
+ * returned non-nil and the accelerator is a candidate for the server.  Results stay
+ * resident on the device for wva_solve.  out / feasible may be NULL (device only). */
+int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible);
+
+/* Candidate sweep (north_star): for every (server, accelerator, replicas r in 1..r_max,
+ * batch b in 1..b_max) evaluate
+ *     analyzer.NewQueueAnalyzer({MaxBatchSize b, MaxQueueSize 10 b}, {in, out})  (queueanalyzer.go:87-131)
+ *     .Analyze(totalRate / float32(r))                                            (queueanalyzer.go:134-174)
+ * with totalRate as in allocation.go:134-139, test the SLOs, and reduce per server to the
+ * feasible candidate of minimum (value, accelerator, replicas, batch), value being the
+ * transition penalty of cost = acc.Cost * float32(numInstances * r).
+ *   best    [S]                 per-server winner (may be NULL)
+ *   cube    [S*A*r_max*b_max]   full metrics, index ((s*A+a)*r_max+(r-1))*b_max+(b-1)  (may be NULL)
+ *   status  [S*A*r_max*b_max]   WVA_CAND_* per candidate                                (may be NULL)
+ * cube/status are HOST pointers; use wva_analyze_grid_device to keep them in HBM. */
+int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max,
+                     wva_grid_best* best, wva_metrics* cube, uint8_t* status);
+
+/* Same sweep, results left in HBM (cube only materialised when want_cube != 0).
+ * wva_grid_fetch copies the per-server winners to the host. */
+int wva_analyze_grid_device(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube);
+int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best);
+
+/* ---- Optimize ------------------------------------------------------------ */
+
+/* Replaces solver.Solver.Solve (pkg/solver/solver.go:32-60): SolveUnlimited (:63-79) or
+ * SolveGreedy (pkg/solver/greedy.go:35-341) over the candidates of the last
+ * wva_analyze_pairs.  chosen_acc[s] = key of the chosen candidate in allAllocations
+ * (accelerator index) or -1 when the server received no allocation; chosen = a copy of
+ * the chosen core.Allocation (after best-effort scaling, greedy.go:208-212, :302-311).
+ * Canonical tie-break: ascending accelerator index, ascending server index. */
+int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec,
+              int32_t* chosen_acc, wva_alloc_soa* chosen);
+
+/* Replaces System.AllocateByType (pkg/core/system.go:271-300): per accelerator type
+ * count += replicas*numInstances*multiplicity, cost += alloc.cost over this rank's shard.
+ * The sums are left in a device buffer (wva_type_totals_device) so the host can run the
+ * one NCCL allreduce of the path on it in place; this call returns the LOCAL totals. */
+int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost);
+
+/* Device address of the {int64 count[T]; then float cost[T]} totals written by the last
+ * wva_allocate_by_type: count at ptr, cost at ptr + 8*T bytes.  The device sum uses a
+ * fixed order (ascending server index) — Go sums in random map order (system.go:273,297). */
+int wva_type_totals_device(wva_ctx* ctx, void** dev_ptr, size_t* bytes);
+
+/* optimizer.SolutionTimeMsec (pkg/solver/optimizer.go:30-34): device+host time of the
+ * last wva_solve in microseconds. */
+int64_t wva_solution_time_usec(const wva_ctx* ctx);
+
+/* ---- low-level analyzer API (pkg/analyzer public surface) ------------------ */
+
+typedef struct wva_queue_config {  /* analyzer.Configuration + RequestSize */
+    int32_t max_batch_size;
+    int32_t max_queue_size;
+    float   alpha, beta, gamma, delta;
+    int32_t avg_input_tokens;
+    int32_t avg_output_tokens;
+} wva_queue_config;
+
+/* n independent QueueAnalyzer.Analyze calls (fresh analyzer each), one thread per
+ * request: metrics[i], status[i] (WVA_CAND_OK or WVA_CAND_ERR_*). */
+int wva_queue_analyze(wva_ctx* ctx, int32_t n, const wva_queue_config* cfg,
+                      const float* rate, wva_metrics* metrics, uint8_t* status);
+
+/* n independent QueueAnalyzer.Size calls (queueanalyzer.go:185-255).  target = TTFT, ITL,
+ * TPS triples; rates = RateTargetTTFT/ITL/TPS triples; achieved = TTFT/ITL/TPS triples.
+ * status[i]: 0 ok, 1 = error (target below bounded region / invalid). */
+int wva_queue_size(wva_ctx* ctx, int32_t n, const wva_queue_config* cfg,
+                   const float* target /*3n*/, float* rates /*3n*/, wva_metrics* metrics,
+                   float* achieved /*3n*/, uint8_t* status);
+
+/* ---- instrumentation ----------------------------------------------------- */
+
+/* Kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
+int64_t wva_launch_count(const wva_ctx* ctx);
+/* Device time (CUDA events on the ctx stream) of the last call of each phase, usec. */
+int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase);
+#define WVA_PHASE_UPLOAD 0
+#define WVA_PHASE_PAIRS  1
+#define WVA_PHASE_GRID   2
+#define WVA_PHASE_SOLVE  3
+#define WVA_PHASE_TOTALS 4
+/* Work counters of the last grid sweep: chain steps actually executed and the
+ * algorithmic chain steps (sum over analysable candidates of 2*(11b+1)). */
+int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic,
+                      uint64_t* candidates_ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WVA_B200_H */
