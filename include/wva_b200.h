@@ -218,6 +218,15 @@ int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max,
 int wva_analyze_grid_device(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube);
 int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best);
 
+/* Device addresses of the S*A candidate records of wva_analyze_pairs (dev->... are DEVICE pointers,
+ * server-major, same extents as the host variant).  Multi-GPU limited-capacity mode: each rank
+ * fills its shard rows, the host all-gathers the rows over NCCL in place, then calls
+ * wva_pairs_commit so that wva_solve may run the (sequential, replicated) greedy assignment. */
+int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
+int wva_pairs_commit(wva_ctx* ctx);
+/* Chain-state updates executed by the last wva_analyze_pairs (instrumentation). */
+int wva_pair_steps(wva_ctx* ctx, uint64_t* steps);
+
 /* ---- Optimize ------------------------------------------------------------ */
 
 /* Replaces solver.Solver.Solve (pkg/solver/solver.go:32-60): SolveUnlimited (:63-79) or
@@ -277,10 +286,20 @@ int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase);
 #define WVA_PHASE_GRID   2
 #define WVA_PHASE_SOLVE  3
 #define WVA_PHASE_TOTALS 4
+#define WVA_PHASE_GRID_KERNEL 5   /* the sweep kernel alone (events right around its launch) */
+/* The cudaStream_t every call of this ctx is enqueued on (so a host can record its own events
+ * on it or order other work after it). */
+void* wva_stream(const wva_ctx* ctx);
 /* Work counters of the last grid sweep: chain steps actually executed and the
  * algorithmic chain steps (sum over analysable candidates of 2*(11b+1)). */
 int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic,
                       uint64_t* candidates_ok);
+
+/* Device self-test of the hoisted-reciprocal double division used by the chain kernels: n operand
+ * pairs from a counter-based generator (mode 0: positive a of any exponent / float32-valued b;
+ * 1: arbitrary doubles; 2: moderate exponents) are divided both ways; *mismatches counts results
+ * that differ bitwise from the plain IEEE operator. */
+int wva_selftest_division(wva_ctx* ctx, uint64_t seed, uint64_t n, int mode, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

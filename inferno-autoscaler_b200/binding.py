@@ -1,0 +1,237 @@
+"""ctypes binding of libwva_b200.so (the C-ABI of include/wva_b200.h).
+
+The library holds sm_100a kernels only.  There is no CPU implementation behind this module:
+loading fails loudly when the shared object has not been built, and every compute call fails
+with WvaError(ECUDA) when no B200 is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .image import SystemImage
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libwva_b200.so")
+_lib = None
+
+# every symbol include/wva_b200.h declares (tests/test_abi_symbols.py checks the header against this)
+EXPORTS = [
+    "wva_abi_version", "wva_ctx_create", "wva_ctx_destroy", "wva_last_error", "wva_system_upload", "wva_set_shard",
+    "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_analyze_grid",
+    "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
+    "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream",
+]
+
+
+class WvaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("wva_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libwva_b200.so (built by __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU implementation to fall back to)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        L.wva_abi_version.restype = C.c_int
+        L.wva_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.wva_ctx_destroy.argtypes = [vp]
+        L.wva_ctx_destroy.restype = None
+        L.wva_last_error.argtypes = [vp]
+        L.wva_last_error.restype = C.c_char_p
+        L.wva_system_upload.argtypes = [vp, C.POINTER(abi.SystemSoa)]
+        L.wva_set_shard.argtypes = [vp, i32, i32]
+        L.wva_analyze_pairs.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
+        L.wva_pairs_device.argtypes = [vp, C.POINTER(abi.AllocSoa), C.POINTER(vp)]
+        L.wva_pairs_commit.argtypes = [vp]
+        L.wva_pair_steps.argtypes = [vp, C.POINTER(u64)]
+        L.wva_analyze_grid.argtypes = [vp, i32, i32, vp, vp, vp]
+        L.wva_analyze_grid_device.argtypes = [vp, i32, i32, i32]
+        L.wva_grid_fetch.argtypes = [vp, vp]
+        L.wva_solve.argtypes = [vp, C.POINTER(abi.OptimizerSpec), abi.i32p, C.POINTER(abi.AllocSoa)]
+        L.wva_allocate_by_type.argtypes = [vp, abi.i64p, abi.f32p]
+        L.wva_type_totals_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.wva_solution_time_usec.argtypes = [vp]
+        L.wva_solution_time_usec.restype = i64
+        L.wva_queue_analyze.argtypes = [vp, i32, vp, abi.f32p, vp, abi.u8p]
+        L.wva_queue_size.argtypes = [vp, i32, vp, abi.f32p, abi.f32p, vp, abi.f32p, abi.u8p]
+        L.wva_launch_count.argtypes = [vp]
+        L.wva_launch_count.restype = i64
+        L.wva_phase_time_usec.argtypes = [vp, C.c_int]
+        L.wva_phase_time_usec.restype = i64
+        L.wva_grid_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
+        L.wva_stream.argtypes = [vp]
+        L.wva_stream.restype = vp
+        if L.wva_abi_version() != abi.ABI_VERSION:
+            raise ImportError("libwva_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class Context:
+    """wva_ctx: one CUDA device, one stream, one call in flight."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().wva_ctx_create(int(device), C.byref(self._h))
+        if rc != abi.OK:
+            raise WvaError(rc, lib().wva_last_error(None).decode())
+        self.device = int(device)
+        self.image = None
+
+    def close(self):
+        if self._h:
+            lib().wva_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != abi.OK:
+            raise WvaError(rc, lib().wva_last_error(self._h).decode())
+
+    # ---- system ------------------------------------------------------------------------
+    def upload(self, image: SystemImage):
+        s = image.c_struct()
+        self._ck(lib().wva_system_upload(self._h, C.byref(s)))
+        self.image = image
+        self.first, self.count = 0, image.S
+
+    def set_shard(self, first, count):
+        self._ck(lib().wva_set_shard(self._h, int(first), int(count)))
+        self.first, self.count = int(first), int(count)
+
+    # ---- analyze -----------------------------------------------------------------------
+    def analyze_pairs(self, download=True):
+        """Server.Calculate for the shard.  Returns (AllocArrays[S*A], feasible[S*A]) (rows outside the
+        shard are zero) or None when download is False (results stay on the device)."""
+        if not download:
+            self._ck(lib().wva_analyze_pairs(self._h, None, None))
+            return None
+        n = self.image.S * self.image.A
+        out = abi.AllocArrays(n)
+        feasible = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().wva_analyze_pairs(self._h, C.byref(out.c), abi.ptr(feasible, C.c_uint8)))
+        return out, feasible
+
+    def pair_steps(self):
+        v = C.c_uint64(0)
+        self._ck(lib().wva_pair_steps(self._h, C.byref(v)))
+        return v.value
+
+    def pairs_device(self):
+        """Device pointers of the candidate records: dict field -> (address, numpy dtype), plus 'feasible'."""
+        dev = abi.AllocSoa()
+        fe = C.c_void_p()
+        self._ck(lib().wva_pairs_device(self._h, C.byref(dev), C.byref(fe)))
+        out = {}
+        for name, dt in abi.ALLOC_FIELDS:
+            out[name] = (C.cast(getattr(dev, name), C.c_void_p).value, np.dtype(dt))
+        out["feasible"] = (fe.value, np.dtype(np.uint8))
+        return out
+
+    def pairs_commit(self):
+        self._ck(lib().wva_pairs_commit(self._h))
+
+    def analyze_grid(self, r_max, b_max, want_cube=False):
+        """Candidate sweep over the shard.  Returns (best[count], cube|None, status|None)."""
+        ns = self.count
+        best = np.zeros(ns, dtype=abi.GRID_BEST_DTYPE)
+        ncand = ns * self.image.A * r_max * b_max
+        cube = np.zeros(ncand, dtype=abi.METRICS_DTYPE) if want_cube else None
+        status = np.zeros(ncand, dtype=np.uint8) if want_cube else None
+        self._ck(lib().wva_analyze_grid(self._h, int(r_max), int(b_max), best.ctypes.data,
+                                        cube.ctypes.data if want_cube else None,
+                                        status.ctypes.data if want_cube else None))
+        return best, cube, status
+
+    def analyze_grid_device(self, r_max, b_max, want_cube=False):
+        self._ck(lib().wva_analyze_grid_device(self._h, int(r_max), int(b_max), 1 if want_cube else 0))
+
+    def grid_fetch(self):
+        best = np.zeros(self.count, dtype=abi.GRID_BEST_DTYPE)
+        self._ck(lib().wva_grid_fetch(self._h, best.ctypes.data))
+        return best
+
+    def grid_counters(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._ck(lib().wva_grid_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(steps_executed=a.value, steps_algorithmic=b.value, candidates_ok=c.value)
+
+    # ---- optimize ----------------------------------------------------------------------
+    def solve(self, unlimited=True, delayed_best_effort=False, policy=abi.POLICY_NONE, download=True):
+        """Solver.Solve.  Returns (chosen_acc[S], AllocArrays[S])."""
+        spec = abi.OptimizerSpec(1 if unlimited else 0, 1 if delayed_best_effort else 0, int(policy))
+        if not download:
+            self._ck(lib().wva_solve(self._h, C.byref(spec), None, None))
+            return None
+        chosen_acc = np.full(self.image.S, -1, dtype=np.int32)
+        chosen = abi.AllocArrays(self.image.S)
+        self._ck(lib().wva_solve(self._h, C.byref(spec), abi.ptr(chosen_acc, C.c_int32), C.byref(chosen.c)))
+        return chosen_acc, chosen
+
+    def allocate_by_type(self):
+        count = np.zeros(self.image.T, dtype=np.int64)
+        cost = np.zeros(self.image.T, dtype=np.float32)
+        self._ck(lib().wva_allocate_by_type(self._h, abi.ptr(count, C.c_int64), abi.ptr(cost, C.c_float)))
+        return count, cost
+
+    def type_totals_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(lib().wva_type_totals_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def solution_time_usec(self):
+        return int(lib().wva_solution_time_usec(self._h))
+
+    # ---- pkg/analyzer batched API ----------------------------------------------------
+    def queue_analyze(self, cfgs, rates):
+        cfgs = np.ascontiguousarray(cfgs, dtype=abi.QUEUE_CONFIG_DTYPE)
+        rates = np.ascontiguousarray(rates, dtype=np.float32)
+        n = len(cfgs)
+        metrics = np.zeros(n, dtype=abi.METRICS_DTYPE)
+        status = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().wva_queue_analyze(self._h, n, cfgs.ctypes.data, abi.ptr(rates, C.c_float), metrics.ctypes.data,
+                                         abi.ptr(status, C.c_uint8)))
+        return metrics, status
+
+    def queue_size(self, cfgs, targets):
+        cfgs = np.ascontiguousarray(cfgs, dtype=abi.QUEUE_CONFIG_DTYPE)
+        targets = np.ascontiguousarray(targets, dtype=np.float32).reshape(-1)
+        n = len(cfgs)
+        rates = np.zeros(3 * n, dtype=np.float32)
+        achieved = np.zeros(3 * n, dtype=np.float32)
+        metrics = np.zeros(n, dtype=abi.METRICS_DTYPE)
+        status = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().wva_queue_size(self._h, n, cfgs.ctypes.data, abi.ptr(targets, C.c_float), abi.ptr(rates, C.c_float),
+                                      metrics.ctypes.data, abi.ptr(achieved, C.c_float), abi.ptr(status, C.c_uint8)))
+        return rates.reshape(n, 3), metrics, achieved.reshape(n, 3), status
+
+    # ---- instrumentation ---------------------------------------------------------------
+    def launch_count(self):
+        return int(lib().wva_launch_count(self._h))
+
+    def phase_usec(self, phase):
+        return int(lib().wva_phase_time_usec(self._h, int(phase)))
+
+    def stream(self):
+        """cudaStream_t (as int) all work of this ctx is enqueued on."""
+        return int(lib().wva_stream(self._h) or 0)
+
+    def selftest_division(self, seed, n, mode):
+        bad = C.c_uint64(0)
+        self._ck(lib().wva_selftest_division(self._h, int(seed), int(n), int(mode), C.byref(bad)))
+        return bad.value

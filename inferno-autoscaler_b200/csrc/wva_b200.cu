@@ -1,0 +1,782 @@
+// wva_b200.cu — C-ABI (include/wva_b200.h) over the sm_100a kernels.
+//
+// One ctx = one CUDA device + one stream.  All entry points launch kernels; there is no host
+// implementation of any arithmetic in this file (and no fallback when CUDA is unavailable).
+#include "wva_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wva;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes < 4096 ? 4096 : bytes);
+        if (e == cudaSuccess) cap = bytes < 4096 ? 4096 : bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct wva_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int64_t phase_usec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // system image
+    bool have_system = false;
+    DevSystem dsys{};
+    DevBuf arena;
+    PinnedBuf staging;
+    int S = 0, A = 0, M = 0, T = 0;
+    int s0 = 0, ns = 0;
+
+    // pair results (full S*A extent; a rank fills its shard rows)
+    DevBuf pairBuf; DevAllocs pairs{}; unsigned char* feasible = nullptr;
+    bool pairs_valid = false; bool pairs_complete = false;
+    DevBuf pairN, pairOrder, pairHist, slowList, slowCount, stepCounter, scratch, scratchOff;
+
+    // solution
+    DevBuf chosenBuf; DevAllocs chosen{}; int* chosen_acc = nullptr; bool solved = false;
+    DevBuf totals;
+    DevBuf greedyBuf;
+
+    // grid
+    DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
+    int grid_r = 0, grid_b = 0; bool grid_valid = false;
+    uint64_t grid_counters[3] = {0, 0, 0};
+
+    // misc io buffers for the low-level API
+    DevBuf ioA, ioB, ioC, ioD, ioE, ioF, ioG;
+};
+
+namespace {
+
+int fail(wva_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(ctx, WVA_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+#define LAUNCH_CHECK()                                                                             \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) return fail(ctx, WVA_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct PhaseTimer {
+    wva_ctx* c; int phase;
+    PhaseTimer(wva_ctx* c_, int p) : c(c_), phase(p) { cudaEventRecord(c->ev0, c->stream); }
+    // call after the stream has been synchronised (or will be by the event sync below)
+    void stop() {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->phase_usec[phase] = (int64_t)(ms * 1000.0f + 0.5f);
+    }
+};
+
+// carve a DevAllocs of n records out of one buffer
+cudaError_t carve_allocs(DevBuf& buf, size_t n, DevAllocs& a, unsigned char** feasible, int** chosen_acc) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_rep = take(n * 8), o_bat = take(n * 8), o_acc = take(n * 4), o_cost = take(n * 4), o_val = take(n * 4),
+           o_itl = take(n * 4), o_ttft = take(n * 4), o_rho = take(n * 4), o_arr = take(n * 4), o_fe = take(n),
+           o_ch = take(n * 4);
+    cudaError_t e = buf.ensure(off);
+    if (e != cudaSuccess) return e;
+    char* b = buf.as<char>();
+    a.num_replicas = (long long*)(b + o_rep); a.batch_size = (long long*)(b + o_bat); a.acc = (int*)(b + o_acc);
+    a.cost = (float*)(b + o_cost); a.value = (float*)(b + o_val); a.itl = (float*)(b + o_itl);
+    a.ttft = (float*)(b + o_ttft); a.rho = (float*)(b + o_rho); a.max_arrv = (float*)(b + o_arr);
+    if (feasible) *feasible = (unsigned char*)(b + o_fe);
+    if (chosen_acc) *chosen_acc = (int*)(b + o_ch);
+    return cudaSuccess;
+}
+
+cudaError_t download_allocs(wva_ctx* ctx, const DevAllocs& d, size_t first, size_t n, wva_alloc_soa* h, size_t hfirst) {
+    cudaError_t e;
+#define DL(field, dfield, T)                                                                                         \
+    if (h->field) {                                                                                                  \
+        e = cudaMemcpyAsync(h->field + hfirst, d.dfield + first, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream); \
+        if (e != cudaSuccess) return e;                                                                              \
+    }
+    DL(acc, acc, int32_t) DL(num_replicas, num_replicas, int64_t) DL(batch_size, batch_size, int64_t)
+    DL(cost, cost, float) DL(value, value, float) DL(itl, itl, float) DL(ttft, ttft, float) DL(rho, rho, float)
+    DL(max_arrv_rate_per_replica, max_arrv, float)
+#undef DL
+    return cudaSuccess;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wva_abi_version(void) { return WVA_ABI_VERSION; }
+
+const char* wva_last_error(const wva_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int wva_ctx_create(int device, wva_ctx** out) {
+    wva_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, WVA_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, WVA_ECUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    if (device < 0 || device >= n) return fail(nullptr, WVA_EINVAL, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, WVA_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, WVA_ECUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, WVA_ECUDA, "device is not sm_100 class; this library carries sm_100a code only");
+    ctx = new wva_ctx;
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess) {
+        std::string msg = std::string("stream/event create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return fail(nullptr, WVA_ECUDA, msg);
+    }
+    *out = ctx;
+    return WVA_OK;
+}
+
+void wva_ctx_destroy(wva_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
+                      &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->chosenBuf, &ctx->totals,
+                      &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
+                      &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->ioA, &ctx->ioB,
+                      &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG};
+    for (DevBuf* b : bufs) b->release();
+    ctx->staging.release();
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->evk0);
+    cudaEventDestroy(ctx->evk1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* wva_stream(const wva_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t wva_launch_count(const wva_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase) { return (ctx && phase >= 0 && phase < 8) ? ctx->phase_usec[phase] : 0; }
+int64_t wva_solution_time_usec(const wva_ctx* ctx) { return ctx ? ctx->phase_usec[WVA_PHASE_SOLVE] : 0; }
+
+// ---------------------------------------------------------------------------------------------
+int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
+    if (!ctx || !h) return fail(ctx, WVA_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int S = h->n_servers, A = h->n_accels, M = h->n_models, T = h->n_types;
+    if (S < 0 || A <= 0 || M < 0 || T <= 0) return fail(ctx, WVA_EINVAL, "bad dimensions");
+    if ((size_t)S * (size_t)A > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "S*A exceeds 2^31-1");
+    // validation of the index arrays (cheap, host side; no arithmetic of the path happens here)
+    for (int a = 0; a < A; ++a)
+        if (h->acc_type[a] < 0 || h->acc_type[a] >= T) return fail(ctx, WVA_EINVAL, "acc_type out of range");
+    for (int s = 0; s < S; ++s) {
+        if (h->srv_model[s] >= M) return fail(ctx, WVA_EINVAL, "srv_model out of range");
+        if (h->srv_cur_acc[s] < WVA_ACC_UNKNOWN || h->srv_cur_acc[s] >= A) return fail(ctx, WVA_EINVAL, "srv_cur_acc out of range");
+        if (h->srv_priority[s] < 1 || h->srv_priority[s] > 100)
+            return fail(ctx, WVA_EINVAL, "srv_priority must be in [1,100] (Server.Priority(), serviceclass.go:28-37)");
+    }
+    PhaseTimer timer(ctx, WVA_PHASE_UPLOAD);
+    struct Item { const void* src; size_t bytes; size_t off; };
+    std::vector<Item> items;
+    size_t off = 0;
+    auto add = [&](const void* src, size_t bytes) { items.push_back({src, bytes, off}); size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t MA = (size_t)M * A;
+    size_t o_acc_cost = add(h->acc_cost, A * 4), o_acc_mult = add(h->acc_multiplicity, A * 4), o_acc_type = add(h->acc_type, A * 4);
+    size_t o_cap = add(h->type_capacity, (size_t)T * 8);
+    size_t o_pa = add(h->perf_alpha, MA * 4), o_pb = add(h->perf_beta, MA * 4), o_pg = add(h->perf_gamma, MA * 4), o_pd = add(h->perf_delta, MA * 4);
+    size_t o_pmb = add(h->perf_max_batch, MA * 4), o_pat = add(h->perf_at_tokens, MA * 4), o_pac = add(h->perf_acc_count, MA * 4), o_pv = add(h->perf_valid, MA);
+    size_t o_sm = add(h->srv_model, (size_t)S * 4), o_sar = add(h->srv_arrival_rpm, (size_t)S * 4), o_sin = add(h->srv_in_tokens, (size_t)S * 4),
+           o_sout = add(h->srv_out_tokens, (size_t)S * 4), o_stt = add(h->srv_slo_ttft, (size_t)S * 4), o_sit = add(h->srv_slo_itl, (size_t)S * 4),
+           o_stp = add(h->srv_slo_tps, (size_t)S * 4), o_stv = add(h->srv_target_valid, (size_t)S), o_spr = add(h->srv_priority, (size_t)S * 4),
+           o_smr = add(h->srv_min_replicas, (size_t)S * 4), o_smb = add(h->srv_max_batch, (size_t)S * 4), o_ska = add(h->srv_keep_acc, (size_t)S),
+           o_sca = add(h->srv_cur_acc, (size_t)S * 4), o_scr = add(h->srv_cur_replicas, (size_t)S * 4), o_scc = add(h->srv_cur_cost, (size_t)S * 4);
+    const size_t total = off;
+    CK(ctx->arena.ensure(total));
+    CK(ctx->staging.ensure(total));
+    char* st = (char*)ctx->staging.p;
+    for (const Item& it : items) if (it.bytes) std::memcpy(st + it.off, it.src, it.bytes);
+    CK(cudaMemcpyAsync(ctx->arena.p, st, total, cudaMemcpyHostToDevice, ctx->stream));
+    char* d = ctx->arena.as<char>();
+    DevSystem& ds = ctx->dsys;
+    ds.S = S; ds.A = A; ds.M = M; ds.T = T;
+    ds.acc_cost = (const float*)(d + o_acc_cost); ds.acc_multiplicity = (const int*)(d + o_acc_mult); ds.acc_type = (const int*)(d + o_acc_type);
+    ds.type_capacity = (const long long*)(d + o_cap);
+    ds.perf_alpha = (const float*)(d + o_pa); ds.perf_beta = (const float*)(d + o_pb); ds.perf_gamma = (const float*)(d + o_pg); ds.perf_delta = (const float*)(d + o_pd);
+    ds.perf_max_batch = (const int*)(d + o_pmb); ds.perf_at_tokens = (const int*)(d + o_pat); ds.perf_acc_count = (const int*)(d + o_pac); ds.perf_valid = (const unsigned char*)(d + o_pv);
+    ds.srv_model = (const int*)(d + o_sm); ds.srv_arrival_rpm = (const float*)(d + o_sar); ds.srv_in_tokens = (const int*)(d + o_sin); ds.srv_out_tokens = (const int*)(d + o_sout);
+    ds.srv_slo_ttft = (const float*)(d + o_stt); ds.srv_slo_itl = (const float*)(d + o_sit); ds.srv_slo_tps = (const float*)(d + o_stp); ds.srv_target_valid = (const unsigned char*)(d + o_stv);
+    ds.srv_priority = (const int*)(d + o_spr); ds.srv_min_replicas = (const int*)(d + o_smr); ds.srv_max_batch = (const int*)(d + o_smb); ds.srv_keep_acc = (const unsigned char*)(d + o_ska);
+    ds.srv_cur_acc = (const int*)(d + o_sca); ds.srv_cur_replicas = (const int*)(d + o_scr); ds.srv_cur_cost = (const float*)(d + o_scc);
+    ctx->S = S; ctx->A = A; ctx->M = M; ctx->T = T;
+    ctx->s0 = 0; ctx->ns = S;
+    ctx->have_system = true;
+    ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
+    timer.stop();
+    return WVA_OK;
+}
+
+int wva_set_shard(wva_ctx* ctx, int32_t first, int32_t count) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    if (first < 0 || count < 0 || first + count > ctx->S) return fail(ctx, WVA_EINVAL, "shard out of range");
+    ctx->s0 = first; ctx->ns = count;
+    ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
+    return WVA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const int A = ctx->A;
+    const size_t nAll = (size_t)ctx->S * A;
+    const int nPairs = ctx->ns * A;
+    CK(carve_allocs(ctx->pairBuf, nAll ? nAll : 1, ctx->pairs, &ctx->feasible, nullptr));
+    CK(ctx->slowList.ensure((size_t)(nPairs ? nPairs : 1) * 4));
+    CK(ctx->slowCount.ensure(4));
+    CK(ctx->stepCounter.ensure(8));
+    CK(ctx->pairN.ensure((size_t)(nPairs ? nPairs : 1) * 8));
+    PhaseTimer timer(ctx, WVA_PHASE_PAIRS);
+    CK(cudaMemsetAsync(ctx->slowCount.p, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stepCounter.p, 0, 8, ctx->stream));
+    int slow = 0;
+    if (nPairs > 0) {
+        k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
+        LAUNCH_CHECK();
+        const int* order = nullptr;
+        if (nPairs > 1024) {
+            // order pairs by chain length (bucket = bit length of N, heaviest first) so that the lanes
+            // of a warp run chains of similar length
+            CK(ctx->pairOrder.ensure((size_t)nPairs * 4));
+            CK(ctx->pairHist.ensure(2 * 65 * 4));
+            CK(cudaMemsetAsync(ctx->pairHist.p, 0, 2 * 65 * 4, ctx->stream));
+            int* hist = ctx->pairHist.as<int>();
+            k_pair_bucket_hist<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->pairN.as<long long>(), nPairs, hist);
+            LAUNCH_CHECK();
+            int hh[65];
+            CK(cudaMemcpyAsync(hh, hist, 65 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            int cur[65]; int run = 0;
+            for (int b = 64; b >= 0; --b) { cur[b] = run; run += hh[b]; }
+            CK(cudaMemcpyAsync(hist + 65, cur, 65 * 4, cudaMemcpyHostToDevice, ctx->stream));
+            k_pair_bucket_scatter<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->pairN.as<long long>(), nPairs, hist + 65,
+                                                                                   ctx->pairOrder.as<int>());
+            LAUNCH_CHECK();
+            order = ctx->pairOrder.as<int>();
+        }
+        k_pairs<<<(nPairs + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, order, ctx->pairs, ctx->feasible,
+                                                              ctx->slowList.as<int>(), ctx->slowCount.as<int>(),
+                                                              ctx->stepCounter.as<unsigned long long>());
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(&slow, ctx->slowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (slow > 0) {
+        // pairs whose chain hit an overflow-rescale branch: re-run with p[] materialised in HBM
+        std::vector<int> list((size_t)slow);
+        CK(cudaMemcpy(list.data(), ctx->slowList.p, (size_t)slow * 4, cudaMemcpyDeviceToHost));
+        std::vector<long long> nAllPairs((size_t)nPairs);
+        CK(cudaMemcpy(nAllPairs.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost));
+        std::vector<long long> offs((size_t)slow);
+        long long total = 0;
+        for (int i = 0; i < slow; ++i) {
+            long long N = nAllPairs[(size_t)list[(size_t)i]];
+            if (N > (1LL << 32)) return fail(ctx, WVA_EINVAL, "pair needs the materialised path with an unreasonably large batch size");
+            offs[(size_t)i] = total;
+            total += 11 * N + 1;
+        }
+        size_t freeB = 0, totB = 0;
+        CK(cudaMemGetInfo(&freeB, &totB));
+        if ((size_t)total * 8 > freeB / 2) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
+        CK(ctx->scratch.ensure((size_t)total * 8));
+        CK(ctx->scratchOff.ensure((size_t)slow * 8));
+        CK(cudaMemcpyAsync(ctx->scratchOff.p, offs.data(), (size_t)slow * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_pairs_literal<<<(slow + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->slowList.as<int>(), slow,
+                                                                 ctx->scratch.as<double>(), ctx->scratchOff.as<long long>(),
+                                                                 ctx->pairs, ctx->feasible, ctx->stepCounter.as<unsigned long long>());
+        LAUNCH_CHECK();
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    timer.stop();
+    ctx->pairs_valid = true;
+    ctx->pairs_complete = (ctx->s0 == 0 && ctx->ns == ctx->S);
+    ctx->solved = false;
+    if (nPairs > 0 && (out || feasible)) {
+        const size_t first = (size_t)ctx->s0 * A;
+        if (out) CK(download_allocs(ctx, ctx->pairs, first, (size_t)nPairs, out, first));
+        if (feasible) CK(cudaMemcpyAsync(feasible + first, ctx->feasible + first, (size_t)nPairs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return WVA_OK;
+}
+
+// device addresses of the pair results (for the host-side NCCL all-gather of limited mode)
+int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible) {
+    if (!ctx || !dev) return WVA_EINVAL;
+    if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "analyze_pairs has not run");
+    dev->acc = ctx->pairs.acc; dev->num_replicas = (int64_t*)ctx->pairs.num_replicas; dev->batch_size = (int64_t*)ctx->pairs.batch_size;
+    dev->cost = ctx->pairs.cost; dev->value = ctx->pairs.value; dev->itl = ctx->pairs.itl; dev->ttft = ctx->pairs.ttft;
+    dev->rho = ctx->pairs.rho; dev->max_arrv_rate_per_replica = ctx->pairs.max_arrv;
+    if (feasible) *feasible = ctx->feasible;
+    return WVA_OK;
+}
+// the host gathered every rank's rows into the device arrays: all S*A records are now valid
+int wva_pairs_commit(wva_ctx* ctx) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "analyze_pairs has not run");
+    ctx->pairs_complete = true;
+    return WVA_OK;
+}
+int wva_pair_steps(wva_ctx* ctx, uint64_t* steps) {
+    if (!ctx || !steps) return WVA_EINVAL;
+    if (!ctx->stepCounter.p) { *steps = 0; return WVA_OK; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(steps, ctx->stepCounter.p, 8, cudaMemcpyDeviceToHost));
+    return WVA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool want_status) {
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    if (r_max < 1 || r_max > WVA_GRID_MAX_R || b_max < 1 || b_max > WVA_GRID_MAX_B || ctx->A > WVA_GRID_MAX_A)
+        return fail(ctx, WVA_EINVAL, "grid extents out of range (A<=256, r_max<=1024, b_max<=8192)");
+    CK(cudaSetDevice(ctx->device));
+    const int ns = ctx->ns, A = ctx->A;
+    const size_t nPairs = (size_t)ns * A;
+    const size_t nCand = nPairs * (size_t)r_max * (size_t)b_max;
+    CK(ctx->keys.ensure((size_t)(ns ? ns : 1) * 8));
+    CK(ctx->bestDev.ensure((size_t)(ns ? ns : 1) * sizeof(wva_grid_best)));
+    CK(ctx->counters.ensure(3 * 8));
+    CK(ctx->gridSlowCount.ensure(4));
+    CK(ctx->faultCount.ensure(4));
+    CK(ctx->faultList.ensure((size_t)(ns ? ns : 1) * 4));
+    int slow_cap = 1 << 16;
+    CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
+    if (want_cube) {
+        size_t freeB = 0, totB = 0;
+        CK(cudaMemGetInfo(&freeB, &totB));
+        if (nCand * sizeof(wva_metrics) > ctx->cube.cap && nCand * sizeof(wva_metrics) > freeB - (freeB >> 3))
+            return fail(ctx, WVA_ECUDA, "metric cube does not fit in device memory");
+        CK(ctx->cube.ensure(nCand * sizeof(wva_metrics)));
+    }
+    if (want_status) CK(ctx->status.ensure(nCand ? nCand : 1));
+
+    GridParams gp;
+    gp.r_max = r_max; gp.b_max = b_max;
+    int n_rchunks = 1;
+    if (nPairs > 0 && nPairs < 2368) {
+        n_rchunks = (int)((2368 + nPairs - 1) / nPairs);
+        if (n_rchunks > r_max) n_rchunks = r_max;
+    }
+    gp.r_chunk = (r_max + n_rchunks - 1) / n_rchunks;
+    gp.n_rchunks = (r_max + gp.r_chunk - 1) / gp.r_chunk;
+    gp.s0 = ctx->s0; gp.ns = ns;
+    gp.cube = want_cube ? ctx->cube.as<wva_metrics>() : nullptr;
+    gp.status = want_status ? ctx->status.as<unsigned char>() : nullptr;
+    gp.keys = ctx->keys.as<unsigned long long>();
+    gp.counters = ctx->counters.as<unsigned long long>();
+    gp.slow_count = ctx->gridSlowCount.as<int>();
+
+    const size_t smem = (size_t)b_max * 20;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t nBlocks = nPairs * (size_t)gp.n_rchunks;
+    if (nBlocks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
+
+    PhaseTimer timer(ctx, WVA_PHASE_GRID);
+    int slow = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
+        CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 4, ctx->stream));
+        if (nBlocks > 0) {
+            CK(cudaEventRecord(ctx->evk0, ctx->stream));
+            k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->stream>>>(ctx->dsys, gp);
+            LAUNCH_CHECK();
+            CK(cudaEventRecord(ctx->evk1, ctx->stream));
+        }
+        CK(cudaMemcpyAsync(&slow, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (nBlocks > 0) {
+            float kms = 0.0f;
+            CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
+            ctx->phase_usec[WVA_PHASE_GRID_KERNEL] = (int64_t)(kms * 1000.0f + 0.5f);
+        }
+        if (slow <= slow_cap) break;
+        slow_cap = slow;                              // rare: more literal-path candidates than the list holds
+        CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
+    }
+    const long long stride = 11LL * b_max + 1;
+    if (slow > 0) {
+        size_t freeB = 0, totB = 0;
+        CK(cudaMemGetInfo(&freeB, &totB));
+        // process the literal list in slices that fit in memory
+        size_t per = (size_t)stride * 8;
+        size_t maxItems = (freeB / 2) / per;
+        if (maxItems == 0) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
+        if (maxItems > (size_t)slow) maxItems = (size_t)slow;
+        CK(ctx->scratch.ensure(maxItems * per));
+        for (size_t done = 0; done < (size_t)slow; done += maxItems) {
+            int n = (int)(((size_t)slow - done) < maxItems ? ((size_t)slow - done) : maxItems);
+            k_grid_literal<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->gridSlow.as<unsigned long long>() + done, n,
+                                                                 ctx->scratch.as<double>(), stride);
+            LAUNCH_CHECK();
+        }
+    }
+    // winners
+    if (ns > 0) {
+        CK(cudaMemsetAsync(ctx->faultCount.p, 0, 4, ctx->stream));
+        k_grid_finalize<<<(ns + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->bestDev.as<wva_grid_best>(), nullptr, 0,
+                                                               nullptr, 0, ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+        LAUNCH_CHECK();
+        int nf = 0;
+        CK(cudaMemcpyAsync(&nf, ctx->faultCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (nf > 0) {
+            CK(ctx->scratch.ensure((size_t)nf * (size_t)stride * 8));
+            CK(ctx->ioG.ensure((size_t)nf * 4));
+            CK(cudaMemcpyAsync(ctx->ioG.p, ctx->faultList.p, (size_t)nf * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            k_grid_finalize<<<(nf + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->bestDev.as<wva_grid_best>(),
+                                                                   ctx->scratch.as<double>(), stride, ctx->ioG.as<int>(), nf,
+                                                                   ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+            LAUNCH_CHECK();
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->grid_counters, ctx->counters.p, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    timer.stop();
+    ctx->grid_r = r_max; ctx->grid_b = b_max; ctx->grid_valid = true;
+    return WVA_OK;
+}
+
+int wva_analyze_grid_device(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube) {
+    if (!ctx) return WVA_EINVAL;
+    return grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0);
+}
+
+int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best) {
+    if (!ctx || !best) return WVA_EINVAL;
+    if (!ctx->grid_valid) return fail(ctx, WVA_ESTATE, "no grid sweep has run");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->ns > 0) {
+        CK(cudaMemcpyAsync(best, ctx->bestDev.p, (size_t)ctx->ns * sizeof(wva_grid_best), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return WVA_OK;
+}
+
+int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max, wva_grid_best* best, wva_metrics* cube, uint8_t* status) {
+    if (!ctx) return WVA_EINVAL;
+    int rc = grid_run(ctx, r_max, b_max, cube != nullptr, status != nullptr);
+    if (rc != WVA_OK) return rc;
+    const size_t nCand = (size_t)ctx->ns * ctx->A * (size_t)r_max * (size_t)b_max;
+    if (best && ctx->ns > 0) CK(cudaMemcpyAsync(best, ctx->bestDev.p, (size_t)ctx->ns * sizeof(wva_grid_best), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cube && nCand) CK(cudaMemcpyAsync(cube, ctx->cube.p, nCand * sizeof(wva_metrics), cudaMemcpyDeviceToHost, ctx->stream));
+    if (status && nCand) CK(cudaMemcpyAsync(status, ctx->status.p, nCand, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WVA_OK;
+}
+
+int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic, uint64_t* candidates_ok) {
+    if (!ctx) return WVA_EINVAL;
+    if (steps_executed) *steps_executed = ctx->grid_counters[0];
+    if (steps_algorithmic) *steps_algorithmic = ctx->grid_counters[1];
+    if (candidates_ok) *candidates_ok = ctx->grid_counters[2];
+    return WVA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc, wva_alloc_soa* chosen) {
+    if (!ctx || !spec) return fail(ctx, WVA_EINVAL, "null argument");
+    if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "wva_solve needs wva_analyze_pairs first");
+    CK(cudaSetDevice(ctx->device));
+    const int S = ctx->S, A = ctx->A, T = ctx->T;
+    CK(carve_allocs(ctx->chosenBuf, (size_t)(S ? S : 1), ctx->chosen, nullptr, &ctx->chosen_acc));
+    PhaseTimer timer(ctx, WVA_PHASE_SOLVE);
+    int first = 0, count = S;
+    if (spec->unlimited) {
+        first = ctx->s0; count = ctx->ns;          // separable: a rank solves its own servers
+        if (count > 0) {
+            k_solve_unlimited<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, first, count, ctx->pairs, ctx->feasible,
+                                                                          ctx->chosen_acc, ctx->chosen);
+            LAUNCH_CHECK();
+        }
+    } else {
+        if (!ctx->pairs_complete)
+            return fail(ctx, WVA_ESTATE, "limited-capacity solve needs the candidates of every server (gather them, then wva_pairs_commit)");
+        // carve greedy buffers
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        const size_t nS = (size_t)(S ? S : 1);
+        size_t o_order = take(nS * A * 4), o_n = take(nS * 4), o_ci = take(nS * 4), o_d = take(nS * 4), o_st = take(nS * 4),
+               o_heap = take(nS * 4), o_gs = take(104 * 4), o_gi = take(nS * 4), o_un = take(nS * 4), o_ta = take(nS * 4),
+               o_tr = take(nS * 4), o_ts = take(nS), o_av = take((size_t)T * 8), o_nan = take(4), o_key = take(nS * 4);
+        CK(ctx->greedyBuf.ensure(off));
+        char* b = ctx->greedyBuf.as<char>();
+        GreedyBufs g;
+        g.order = (int*)(b + o_order); g.nCand = (int*)(b + o_n); g.curIndex = (int*)(b + o_ci); g.delta = (float*)(b + o_d);
+        g.stamp = (int*)(b + o_st); g.heap = (int*)(b + o_heap); g.groupStart = (int*)(b + o_gs); g.groupItems = (int*)(b + o_gi);
+        g.unalloc = (int*)(b + o_un); g.ticketAcc = (int*)(b + o_ta); g.ticketRep = (int*)(b + o_tr);
+        g.ticketState = (unsigned char*)(b + o_ts); g.available = (long long*)(b + o_av); g.nanFlag = (int*)(b + o_nan);
+        int* chosenKey = (int*)(b + o_key);
+        CK(cudaMemsetAsync(g.groupStart, 0, 104 * 4, ctx->stream));
+        CK(cudaMemsetAsync(g.nanFlag, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(chosenKey, 0xff, nS * 4, ctx->stream));
+        if (S > 0) {
+            k_greedy_prepare<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, ctx->feasible, g);
+            LAUNCH_CHECK();
+            k_greedy_bucket_count<<<(S + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, g);
+            LAUNCH_CHECK();
+            int nanFlag = 0;
+            CK(cudaMemcpyAsync(&nanFlag, g.nanFlag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (nanFlag) return fail(ctx, WVA_ENONFINITE, "a candidate value is NaN: the greedy order is undefined");
+            k_greedy_solve<<<1, 32, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, g, chosenKey, spec->delayed_best_effort ? 1 : 0,
+                                                     spec->saturation_policy);
+            LAUNCH_CHECK();
+            k_greedy_collect<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, chosenKey, ctx->chosen_acc, ctx->chosen);
+            LAUNCH_CHECK();
+        }
+        // best-effort scaling mutated the candidate records in place (greedy.go:208-212): the
+        // device copy no longer equals Server.Calculate's output
+        ctx->pairs_valid = false;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    timer.stop();
+    ctx->solved = true;
+    if (count > 0) {
+        if (chosen_acc) CK(cudaMemcpyAsync(chosen_acc + first, ctx->chosen_acc + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (chosen) CK(download_allocs(ctx, ctx->chosen, (size_t)first, (size_t)count, chosen, (size_t)first));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return WVA_OK;
+}
+
+int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->solved) return fail(ctx, WVA_ESTATE, "wva_allocate_by_type needs wva_solve first");
+    CK(cudaSetDevice(ctx->device));
+    const int T = ctx->T;
+    CK(ctx->totals.ensure((size_t)T * 12));
+    PhaseTimer timer(ctx, WVA_PHASE_TOTALS);
+    long long* dcount = ctx->totals.as<long long>();
+    float* dcost = (float*)(ctx->totals.as<char>() + (size_t)T * 8);
+    k_totals<<<(T + 31) / 32, 32, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->ns, ctx->chosen_acc, ctx->chosen, dcount, dcost);
+    LAUNCH_CHECK();
+    timer.stop();
+    if (count) CK(cudaMemcpyAsync(count, dcount, (size_t)T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cost) CK(cudaMemcpyAsync(cost, dcost, (size_t)T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WVA_OK;
+}
+
+int wva_type_totals_device(wva_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr) return WVA_EINVAL;
+    if (!ctx->totals.p) return fail(ctx, WVA_ESTATE, "wva_allocate_by_type has not run");
+    *dev_ptr = ctx->totals.p;
+    if (bytes) *bytes = (size_t)ctx->T * 12;
+    return WVA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// low-level analyzer API
+static int queue_scratch(wva_ctx* ctx, const wva_queue_config* cfg, const std::vector<int>& list, DevBuf& offBuf) {
+    std::vector<long long> offs(list.size());
+    long long total = 0;
+    for (size_t i = 0; i < list.size(); ++i) {
+        const wva_queue_config& c = cfg[list[i]];
+        offs[i] = total;
+        total += (long long)c.max_batch_size + (long long)c.max_queue_size + 1;
+    }
+    size_t freeB = 0, totB = 0;
+    CK(cudaMemGetInfo(&freeB, &totB));
+    if ((size_t)total * 8 > freeB / 2) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
+    CK(ctx->scratch.ensure((size_t)total * 8));
+    CK(offBuf.ensure(list.size() * 8));
+    CK(cudaMemcpyAsync(offBuf.p, offs.data(), list.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return WVA_OK;
+}
+
+int wva_queue_analyze(wva_ctx* ctx, int32_t n, const wva_queue_config* cfg, const float* rate, wva_metrics* metrics, uint8_t* status) {
+    if (!ctx || n < 0 || !cfg || !rate || !metrics || !status) return fail(ctx, WVA_EINVAL, "null argument");
+    if (n == 0) return WVA_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->ioA.ensure((size_t)n * sizeof(wva_queue_config)));
+    CK(ctx->ioB.ensure((size_t)n * 4));
+    CK(ctx->ioC.ensure((size_t)n * sizeof(wva_metrics)));
+    CK(ctx->ioD.ensure((size_t)n));
+    CK(ctx->faultList.ensure((size_t)n * 4));
+    CK(ctx->faultCount.ensure(4));
+    CK(cudaMemcpyAsync(ctx->ioA.p, cfg, (size_t)n * sizeof(wva_queue_config), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ioB.p, rate, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->faultCount.p, 0, 4, ctx->stream));
+    k_queue_analyze<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->ioA.as<wva_queue_config>(), ctx->ioB.as<float>(),
+                                                             ctx->ioC.as<wva_metrics>(), ctx->ioD.as<unsigned char>(), nullptr,
+                                                             nullptr, nullptr, ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+    LAUNCH_CHECK();
+    int nf = 0;
+    CK(cudaMemcpyAsync(&nf, ctx->faultCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nf > 0) {
+        std::vector<int> list((size_t)nf);
+        CK(cudaMemcpy(list.data(), ctx->faultList.p, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+        int rc = queue_scratch(ctx, cfg, list, ctx->scratchOff);
+        if (rc != WVA_OK) return rc;
+        CK(ctx->ioG.ensure((size_t)nf * 4));
+        CK(cudaMemcpyAsync(ctx->ioG.p, list.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_queue_analyze<<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->ioA.as<wva_queue_config>(), ctx->ioB.as<float>(),
+                                                                  ctx->ioC.as<wva_metrics>(), ctx->ioD.as<unsigned char>(),
+                                                                  ctx->scratch.as<double>(), ctx->scratchOff.as<long long>(),
+                                                                  ctx->ioG.as<int>(), ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+        LAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(metrics, ctx->ioC.p, (size_t)n * sizeof(wva_metrics), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ctx->ioD.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WVA_OK;
+}
+
+int wva_queue_size(wva_ctx* ctx, int32_t n, const wva_queue_config* cfg, const float* target, float* rates, wva_metrics* metrics,
+                   float* achieved, uint8_t* status) {
+    if (!ctx || n < 0 || !cfg || !target || !rates || !metrics || !achieved || !status) return fail(ctx, WVA_EINVAL, "null argument");
+    if (n == 0) return WVA_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->ioA.ensure((size_t)n * sizeof(wva_queue_config)));
+    CK(ctx->ioB.ensure((size_t)n * 12));
+    CK(ctx->ioC.ensure((size_t)n * sizeof(wva_metrics)));
+    CK(ctx->ioD.ensure((size_t)n));
+    CK(ctx->ioE.ensure((size_t)n * 12));
+    CK(ctx->ioF.ensure((size_t)n * 12));
+    CK(ctx->faultList.ensure((size_t)n * 4));
+    CK(ctx->faultCount.ensure(4));
+    CK(cudaMemcpyAsync(ctx->ioA.p, cfg, (size_t)n * sizeof(wva_queue_config), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ioB.p, target, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->faultCount.p, 0, 4, ctx->stream));
+    k_queue_size<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->ioA.as<wva_queue_config>(), ctx->ioB.as<float>(), ctx->ioE.as<float>(),
+                                                          ctx->ioC.as<wva_metrics>(), ctx->ioF.as<float>(), ctx->ioD.as<unsigned char>(),
+                                                          nullptr, nullptr, nullptr, ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+    LAUNCH_CHECK();
+    int nf = 0;
+    CK(cudaMemcpyAsync(&nf, ctx->faultCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nf > 0) {
+        std::vector<int> list((size_t)nf);
+        CK(cudaMemcpy(list.data(), ctx->faultList.p, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+        int rc = queue_scratch(ctx, cfg, list, ctx->scratchOff);
+        if (rc != WVA_OK) return rc;
+        CK(ctx->ioG.ensure((size_t)nf * 4));
+        CK(cudaMemcpyAsync(ctx->ioG.p, list.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_queue_size<<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->ioA.as<wva_queue_config>(), ctx->ioB.as<float>(), ctx->ioE.as<float>(),
+                                                               ctx->ioC.as<wva_metrics>(), ctx->ioF.as<float>(), ctx->ioD.as<unsigned char>(),
+                                                               ctx->scratch.as<double>(), ctx->scratchOff.as<long long>(), ctx->ioG.as<int>(),
+                                                               ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+        LAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(rates, ctx->ioE.p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(achieved, ctx->ioF.p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(metrics, ctx->ioC.p, (size_t)n * sizeof(wva_metrics), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ctx->ioD.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WVA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device self-test of the hoisted division: compares div_hoisted(a, b, rcp_refined(b)) with a / b
+// on n operand pairs produced on the device from a counter-based generator; returns the number of
+// mismatching results (bitwise, NaNs compared by class).  Used by tests/test_div_gpu.py.
+}  // extern "C"
+
+namespace wva {
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+__global__ void k_div_selftest(unsigned long long seed, unsigned long long n, int mode, unsigned long long* mismatches) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (; i < n; i += stride) {
+        unsigned long long ra = splitmix64(seed + 2 * i), rb = splitmix64(seed + 2 * i + 1);
+        double a, b;
+        if (mode == 0) {                 // chain-like operands: positive, any exponent; divisor a float32 value
+            a = __longlong_as_double((long long)(ra & 0x7fffffffffffffffULL));
+            float bf = __uint_as_float((unsigned)(rb & 0x7fffffffu));
+            b = (double)bf;
+        } else if (mode == 1) {          // arbitrary doubles (all exponents, both signs)
+            a = __longlong_as_double((long long)ra);
+            b = __longlong_as_double((long long)rb);
+        } else {                         // moderate exponents: the common case of the chain
+            a = __longlong_as_double((long long)((ra & 0x800fffffffffffffULL) | ((0x3ffULL - 40 + (ra >> 52) % 80) << 52)));
+            b = __longlong_as_double((long long)((rb & 0x000fffffffffffffULL) | ((0x3ffULL - 20 + (rb >> 52) % 40) << 52)));
+        }
+        double ref = a / b;
+        double got = divisor_in_window(b) ? div_hoisted(a, b, rcp_refined(b)) : a / b;
+        bool same = (__double_as_longlong(ref) == __double_as_longlong(got)) || (ref != ref && got != got);
+        if (!same) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace wva
+
+extern "C" int wva_selftest_division(wva_ctx* ctx, uint64_t seed, uint64_t n, int mode, uint64_t* mismatches) {
+    if (!ctx || !mismatches) return WVA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->counters.ensure(3 * 8));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 8, ctx->stream));
+    wva::k_div_selftest<<<148 * 8, 256, 0, ctx->stream>>>(seed, n, mode, ctx->counters.as<unsigned long long>());
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(mismatches, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WVA_OK;
+}

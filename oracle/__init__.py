@@ -78,6 +78,11 @@ def lib():
     return _lib
 
 
+def rescale_events():
+    lib().wvao_rescale_events.restype = C.c_uint64
+    return int(lib().wvao_rescale_events())
+
+
 def hardware_threads():
     return int(lib().wvao_hardware_threads())
 

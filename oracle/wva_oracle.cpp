@@ -71,6 +71,7 @@ inline int go_cmpf(float x, float y) {
 }
 inline int go_cmpi(int64_t x, int64_t y) { return x < y ? -1 : (x > y ? +1 : 0); }
 
+std::atomic<uint64_t> g_rescale_events{0};   // instrumentation: overflow-rescale branches taken
 const float kMaxFloat32 = std::numeric_limits<float>::max();
 const double kMaxFloat64 = std::numeric_limits<double>::max();
 
@@ -127,6 +128,7 @@ struct StateDependentModel {
             double t = p[n] * (double)lambda;                                   // :83, (p*lambda)/s
             p[n + 1] = t / sRate;
             while (p[n + 1] < 0 || std::isinf(p[n + 1]) || std::isnan(p[n + 1])) {   // :84
+                g_rescale_events++;
                 for (int64_t i = 0; i <= n; i++) p[i] /= scale;
                 double t2 = p[n] * (double)lambda;
                 p[n + 1] = t2 / sRate;
@@ -136,6 +138,7 @@ struct StateDependentModel {
         for (int64_t n = 0; n <= K; n++) {
             sum += p[n];
             if (sum < 0 || std::isinf(sum)) {                                   // :95
+                g_rescale_events++;
                 sum = 0;
                 for (int64_t i = 0; i <= K; i++) {
                     p[i] /= scale;
@@ -1017,6 +1020,9 @@ int wvao_allocate_by_type(const wva_system_soa* sys, int32_t s0, int32_t s1, con
     }
     return WVA_OK;
 }
+
+// number of overflow-rescale branches (mm1modelstatedependent.go:84-89, :96-104) taken since load
+uint64_t wvao_rescale_events(void) { return g_rescale_events.load(); }
 
 int wvao_hardware_threads(void) { unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
 

@@ -1,0 +1,250 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Bar: bit-exact on every integer and on every float32 (compared through their bit
+patterns).  Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def _assert_allocs_equal(got, want, mask=None):
+    ok, field = got.equal_bits(want, mask)
+    assert ok, "field %s differs" % field
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def test_division_selftest(ctx):
+    """div_hoisted(a, b, rcp_refined(b)) == a / b bitwise (the hoisted-reciprocal division of the chain)."""
+    for mode in (0, 1, 2):
+        assert ctx.selftest_division(1234 + mode, 200_000_000, mode) == 0, mode
+
+
+def test_queue_analyze_matches_oracle(wva, oracle, ctx):
+    rng = np.random.default_rng(11)
+    n = 3000
+    cfg = np.zeros(n, dtype=wva.abi.QUEUE_CONFIG_DTYPE)
+    cfg["max_batch_size"] = rng.integers(1, 200, n)
+    cfg["max_queue_size"] = cfg["max_batch_size"] * rng.integers(0, 12, n)
+    cfg["alpha"] = rng.uniform(1, 30, n); cfg["beta"] = rng.uniform(0.01, 1, n)
+    cfg["gamma"] = rng.uniform(0, 250, n); cfg["delta"] = rng.uniform(0, 0.1, n)
+    cfg["avg_input_tokens"] = rng.integers(0, 3000, n); cfg["avg_output_tokens"] = rng.integers(1, 600, n)
+    # a few invalid configs and edge cases
+    cfg["max_batch_size"][:5] = [0, -1, 1, 1, 2]
+    cfg["max_queue_size"][:5] = [4, 4, 0, 1, -1]
+    cfg["avg_output_tokens"][5:8] = [0, 1, 1]; cfg["avg_input_tokens"][5:8] = [10, 0, 5]
+    _, hi = np.zeros(n, F), np.zeros(n, F)
+    # rates spread over (0, 1.1*max] plus non-positive ones
+    a = oracle.queue_analyze(cfg, np.full(n, 1e-3, F))[0]
+    rates = (a["max_rate"] * rng.uniform(0.0005, 1.1, n)).astype(F)
+    rates[10:14] = [0.0, -1.0, 1e-6, 1e9]
+    want_m, want_s = oracle.queue_analyze(cfg, rates)
+    got_m, got_s = ctx.queue_analyze(cfg, rates)
+    assert np.array_equal(got_s, want_s)
+    assert got_m.tobytes() == want_m.tobytes()
+    assert (want_s == 0).sum() > n // 2
+
+
+def test_queue_size_matches_oracle(wva, oracle, ctx):
+    rng = np.random.default_rng(12)
+    n = 600
+    cfg = np.zeros(n, dtype=wva.abi.QUEUE_CONFIG_DTYPE)
+    cfg["max_batch_size"] = rng.integers(1, 96, n)
+    cfg["max_queue_size"] = cfg["max_batch_size"] * 10
+    cfg["alpha"] = rng.uniform(1, 30, n); cfg["beta"] = rng.uniform(0.01, 1, n)
+    cfg["gamma"] = rng.uniform(0, 250, n); cfg["delta"] = rng.uniform(0, 0.1, n)
+    cfg["avg_input_tokens"] = rng.integers(0, 3000, n); cfg["avg_output_tokens"] = rng.integers(1, 600, n)
+    targets = np.stack([rng.choice([0.0, 50.0, 500.0, 2000.0], n), rng.choice([0.0, 5.0, 24.0, 80.0, 200.0], n),
+                        rng.choice([0.0, 0.0, 100.0], n)], axis=1).astype(F)
+    targets[:3] = [[-1, 5, 0], [50, -1, 0], [50, 5, -1]]
+    want = oracle.queue_size(cfg, targets)
+    got = ctx.queue_size(cfg, targets)
+    assert np.array_equal(got[3], want[3])
+    assert _bits(got[0]).tobytes() == _bits(want[0]).tobytes()
+    assert got[1].tobytes() == want[1].tobytes()
+    assert _bits(got[2]).tobytes() == _bits(want[2]).tobytes()
+    assert (want[3] == 0).sum() > n // 4
+
+
+@pytest.mark.parametrize("seed,S,A", [(21, 300, 4), (22, 64, 8)])
+def test_pairs_match_oracle(wva, oracle, ctx, seed, S, A):
+    img = wva.synth.make_system(S, A, seed=seed, n_types=max(1, A // 2), max_pair_batch=512)
+    ctx.upload(img)
+    got, gfe = ctx.analyze_pairs()
+    want, wfe, steps = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
+    assert np.array_equal(gfe, wfe)
+    _assert_allocs_equal(got, want)
+    assert wfe.sum() > S * A // 3
+    assert ctx.pair_steps() <= steps          # truncation never does more work than the reference
+
+
+def test_pairs_golden_config1(wva, oracle, ctx):
+    """BASELINE config 1 and the survey's derived vectors through the CUDA path."""
+    img = wva.synth.config1()
+    ctx.upload(img)
+    got, fe = ctx.analyze_pairs()
+    assert fe[0] == 1 and got.num_replicas[0] == 5 and got.batch_size[0] == 512 and got.cost[0] == F(160.0)
+    assert got.itl[0] == F(23.991173) and got.ttft[0] == F(243.6568) and got.rho[0] == F(0.012853656)
+    for rpm, mb, rep in [(60.0, 512, 1), (6000.0, 512, 50), (600.0, 8, 7), (600.0, 64, 5), (600.0, 256, 5)]:
+        img.srv_arrival_rpm[0] = rpm; img.srv_max_batch[0] = mb
+        ctx.upload(img)
+        got, fe = ctx.analyze_pairs()
+        assert fe[0] == 1 and got.num_replicas[0] == rep
+    img.srv_arrival_rpm[0] = 600.0; img.srv_max_batch[0] = 1
+    ctx.upload(img)
+    assert ctx.analyze_pairs()[1][0] == 0
+
+
+def test_pairs_overflow_rescale_path(wva, oracle, ctx):
+    """Chains that overflow float64 take the materialised-p[] path (mm1modelstatedependent.go:84-89,
+    :96-104): tiny beta/delta with a large batch make p[n] grow like N^n/n!."""
+    img = wva.synth.make_system(6, 2, seed=5, max_pair_batch=0)
+    img.perf_alpha[:] = 20.0; img.perf_beta[:] = 1e-4; img.perf_gamma[:] = 10.0; img.perf_delta[:] = 1e-7
+    img.perf_valid[:] = 1; img.srv_target_valid[:] = 1
+    img.srv_max_batch[:] = [900, 1500, 2500, 1200, 3000, 2000]
+    img.srv_arrival_rpm[:] = [3e5, 6e5, 2e6, 1e3, 5e6, 9e5]
+    img.srv_in_tokens[:] = 64; img.srv_out_tokens[:] = 8
+    img.srv_slo_itl[:] = 200.0; img.srv_slo_ttft[:] = 2000.0; img.srv_slo_tps[:] = 0.0
+    img.srv_keep_acc[:] = 0
+    ctx.upload(img)
+    got, gfe = ctx.analyze_pairs()
+    want, wfe, _ = oracle.analyze_pairs(img)
+    assert np.array_equal(gfe, wfe)
+    _assert_allocs_equal(got, want)
+    assert wfe.sum() >= 6
+
+
+@pytest.mark.parametrize("seed,S,A,R,B", [(31, 6, 3, 8, 48), (32, 3, 2, 5, 70), (33, 2, 1, 64, 33)])
+def test_grid_matches_oracle(wva, oracle, ctx, seed, S, A, R, B):
+    img = wva.synth.make_system(S, A, seed=seed, zero_load_fraction=0.0)
+    img.srv_arrival_rpm[:] = np.maximum(img.srv_arrival_rpm, 30.0)
+    ctx.upload(img)
+    best, cube, status = ctx.analyze_grid(R, B, want_cube=True)
+    w_best, w_cube, w_status, steps = oracle.analyze_grid(img, R, B, threads=oracle.hardware_threads())
+    assert np.array_equal(status, w_status)
+    assert cube.tobytes() == w_cube.tobytes()
+    assert best.tobytes() == w_best.tobytes()
+    c = ctx.grid_counters()
+    assert c["candidates_ok"] == int(((w_status & 0xfe) == 0).sum())
+    assert c["steps_algorithmic"] == steps and c["steps_executed"] <= steps
+    assert (w_status & 1).sum() > 0 and (w_best["acc"] >= 0).any()
+
+
+def test_grid_config1(wva, oracle, ctx):
+    """BASELINE config 1: 1 model, 1 accelerator, replicas 1-8, batch 1-256."""
+    img = wva.synth.config1()
+    ctx.upload(img)
+    best, cube, status = ctx.analyze_grid(8, 256, want_cube=True)
+    w_best, w_cube, w_status, _ = oracle.analyze_grid(img, 8, 256, threads=oracle.hardware_threads())
+    assert np.array_equal(status, w_status) and cube.tobytes() == w_cube.tobytes() and best.tobytes() == w_best.tobytes()
+    assert best["acc"][0] == 0 and best["replicas"][0] >= 1
+
+
+def test_grid_edge_servers(wva, oracle, ctx):
+    """zero load, out=1, in=0, missing perf/target, keepAccelerator, negative SLO."""
+    img = wva.synth.make_system(8, 2, seed=41)
+    img.perf_valid[:] = 1; img.srv_target_valid[:] = 1
+    img.srv_arrival_rpm[0] = 0.0
+    img.srv_out_tokens[1] = 1; img.srv_in_tokens[1] = 0
+    img.srv_in_tokens[2] = 0
+    img.perf_valid[3 * 2 + 1] = 0
+    img.srv_target_valid[4] = 0
+    img.srv_keep_acc[5] = 1; img.srv_cur_acc[5] = 1
+    img.srv_slo_itl[6] = -1.0
+    img.srv_out_tokens[7] = 0
+    ctx.upload(img)
+    best, cube, status = ctx.analyze_grid(6, 40, want_cube=True)
+    w_best, w_cube, w_status, _ = oracle.analyze_grid(img, 6, 40)
+    assert np.array_equal(status, w_status) and cube.tobytes() == w_cube.tobytes() and best.tobytes() == w_best.tobytes()
+
+
+def _capacity_case(wva, oracle, seed, S, A, T, frac):
+    img = wva.synth.make_system(S, A, seed=seed, n_types=T, max_pair_batch=256)
+    pairs, feas, _ = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
+    acc, chosen = oracle.solve(img, pairs, feas, unlimited=True)
+    wva.synth.set_capacity_from_demand(img, chosen.acc, chosen.num_replicas, fraction=frac)
+    return img, pairs, feas
+
+
+def test_solve_unlimited_and_totals(wva, oracle, ctx):
+    img, pairs, feas = _capacity_case(wva, oracle, 51, 400, 6, 3, 0.6)
+    ctx.upload(img)
+    ctx.analyze_pairs(download=False)
+    acc, chosen = ctx.solve(unlimited=True)
+    w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=True)
+    assert np.array_equal(acc, w_acc)
+    _assert_allocs_equal(chosen, w_chosen)
+    count, cost = ctx.allocate_by_type()
+    w_count, w_cost = oracle.allocate_by_type(img, w_acc, w_chosen)
+    assert np.array_equal(count, w_count) and cost.tobytes() == w_cost.tobytes()
+    assert ctx.solution_time_usec() >= 0
+
+
+@pytest.mark.parametrize("policy", [0, 1, 2, 3])
+@pytest.mark.parametrize("delayed", [False, True])
+def test_solve_greedy_policies(wva, oracle, ctx, policy, delayed):
+    img, pairs, feas = _capacity_case(wva, oracle, 52, 500, 6, 3, 0.6)
+    ctx.upload(img)
+    ctx.analyze_pairs(download=False)
+    acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
+    w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
+    assert np.array_equal(acc, w_acc)
+    _assert_allocs_equal(chosen, w_chosen)
+    count, cost = ctx.allocate_by_type()
+    w_count, w_cost = oracle.allocate_by_type(img, w_acc, w_chosen)
+    assert np.array_equal(count, w_count) and cost.tobytes() == w_cost.tobytes()
+    # capacity is respected unless round-robin over-allocation applies (never exceeds capacity either)
+    assert (count <= img.type_capacity).all()
+    assert (w_acc < 0).any() or policy != 0
+
+
+def test_solve_greedy_ties(wva, oracle, ctx):
+    """identical servers: every comparison in the greedy order ties; canonical order = server index."""
+    img = wva.synth.make_system(40, 3, seed=53, n_types=2, one_model_per_server=False, n_models=1)
+    for name, _ in wva.abi.SRV_FIELDS:
+        arr = getattr(img, name); arr[:] = arr[0]
+    img.srv_model[:] = 0; img.perf_valid[:] = 1; img.srv_target_valid[:] = 1
+    img.srv_arrival_rpm[:] = 900.0; img.srv_keep_acc[:] = 0; img.srv_cur_acc[:] = -1; img.srv_cur_cost[:] = 0
+    img.srv_cur_replicas[:] = 0; img.srv_max_batch[:] = 32; img.srv_slo_tps[:] = 0
+    pairs, feas, _ = oracle.analyze_pairs(img)
+    assert feas.all()
+    acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
+    wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.45)
+    for policy in (0, 1, 3):
+        ctx.upload(img)
+        ctx.analyze_pairs(download=False)
+        acc, chosen = ctx.solve(unlimited=False, policy=policy)
+        w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, policy=policy)
+        assert np.array_equal(acc, w_acc)
+        _assert_allocs_equal(chosen, w_chosen)
+
+
+def test_state_errors(wva, ctx):
+    from inferno_autoscaler_b200 import binding
+    img = wva.synth.make_system(4, 2, seed=1)
+    ctx.upload(img)
+    with pytest.raises(binding.WvaError) as e:
+        ctx.solve(unlimited=True)
+    assert e.value.code == wva.abi.ESTATE
+    img.srv_priority[0] = 0
+    with pytest.raises(binding.WvaError) as e:
+        ctx.upload(img)
+    assert e.value.code == wva.abi.EINVAL
+
+
+def test_sharded_pairs_equal_full(wva, oracle, ctx):
+    """server shards are independent: shard-wise analysis concatenates to the full result."""
+    img = wva.synth.make_system(90, 3, seed=61, max_pair_batch=256)
+    ctx.upload(img)
+    full, ffe = ctx.analyze_pairs()
+    A = img.A
+    for first, count in [(0, 30), (30, 45), (75, 15)]:
+        ctx.set_shard(first, count)
+        part, pfe = ctx.analyze_pairs()
+        sl = slice(first * A, (first + count) * A)
+        mask = np.zeros(img.S * A, bool); mask[sl] = True
+        assert np.array_equal(pfe[sl], ffe[sl])
+        _assert_allocs_equal(part, full, mask)
