@@ -243,7 +243,7 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    grid_kernel_us, phase_us = [], {k: [] for k in ("pairs", "grid", "solve", "totals")}
+    grid_kernel_us, phase_us = [], {k: [] for k in ("pairs", "grid", "solve", "totals", "grid_light_kernel", "grid_heavy")}
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         l2_flush.fill_(i & 0xff)                      # evict L2 between timed iterations (not timed)
@@ -252,8 +252,9 @@ def main():
         step_device()
         ev[i][1].record(stream)
         torch.cuda.synchronize()
-        grid_kernel_us.append(ctx.phase_usec(abi.PHASE_GRID_KERNEL))
-        for k, ph in (("pairs", abi.PHASE_PAIRS), ("grid", abi.PHASE_GRID), ("solve", abi.PHASE_SOLVE), ("totals", abi.PHASE_TOTALS)):
+        grid_kernel_us.append(ctx.phase_usec(abi.PHASE_GRID_KERNEL) + ctx.phase_usec(abi.PHASE_GRID_HEAVY))
+        for k, ph in (("pairs", abi.PHASE_PAIRS), ("grid", abi.PHASE_GRID), ("solve", abi.PHASE_SOLVE), ("totals", abi.PHASE_TOTALS),
+                      ("grid_light_kernel", abi.PHASE_GRID_KERNEL), ("grid_heavy", abi.PHASE_GRID_HEAVY)):
             phase_us[k].append(ctx.phase_usec(ph))
     barrier()
     wall = time.perf_counter() - t_wall0
@@ -309,12 +310,13 @@ def main():
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_grid", "kernel_us": k_us,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_grid + k_grid_list (sweep: per-pair kernel + deferred long chains)", "kernel_us": k_us,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the sweep is FP64-issue bound (see fp64); HBM fraction reported because BASELINE.json asks for it"},
             "fp64": {"chain_steps_executed": counters["steps_executed"], "chain_steps_reference": counters["steps_algorithmic"],
                      "truncation_ratio": counters["steps_algorithmic"] / max(1, counters["steps_executed"]),
-                     "fp64_inst_per_s": fp64_ops / (k_us * 1e-6), "candidates_analysed": counters["candidates_ok"]},
+                     "fp64_inst_per_s": fp64_ops / (k_us * 1e-6), "candidates_analysed": counters["candidates_ok"],
+                     "lists": ctx.grid_list_sizes()},
             "phases_ms": {k: float(np.mean(v)) / 1e3 for k, v in phase_us.items()},
             "wall_s_timed_region": wall,
         }

@@ -287,9 +287,16 @@ int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase);
 #define WVA_PHASE_SOLVE  3
 #define WVA_PHASE_TOTALS 4
 #define WVA_PHASE_GRID_KERNEL 5   /* the sweep kernel alone (events right around its launch) */
+#define WVA_PHASE_GRID_HEAVY  6   /* ordering + processing of the deferred long chains */
 /* The cudaStream_t every call of this ctx is enqueued on (so a host can record its own events
  * on it or order other work after it). */
 void* wva_stream(const wva_ctx* ctx);
+/* Sweep tuning: candidates whose chain tail needs more than tail_cap steps are deferred from the
+ * per-pair sweep kernel to a second kernel that groups chains of similar length (0 = never defer).
+ * Results do not depend on it.  wva_grid_list_sizes: how many candidates the last sweep deferred /
+ * sent to the materialised-p[] path. */
+int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap);
+int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal);
 /* Work counters of the last grid sweep: chain steps actually executed and the
  * algorithmic chain steps (sum over analysable candidates of 2*(11b+1)). */
 int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic,

@@ -22,7 +22,7 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes",
 ]
 
 
@@ -69,6 +69,8 @@ def lib():
         L.wva_phase_time_usec.restype = i64
         L.wva_grid_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
+        L.wva_grid_set_tail_cap.argtypes = [vp, i32]
+        L.wva_grid_list_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.wva_stream.argtypes = [vp]
         L.wva_stream.restype = vp
         if L.wva_abi_version() != abi.ABI_VERSION:
@@ -165,6 +167,14 @@ class Context:
         best = np.zeros(self.count, dtype=abi.GRID_BEST_DTYPE)
         self._ck(lib().wva_grid_fetch(self._h, best.ctypes.data))
         return best
+
+    def grid_set_tail_cap(self, cap):
+        self._ck(lib().wva_grid_set_tail_cap(self._h, int(cap)))
+
+    def grid_list_sizes(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(lib().wva_grid_list_sizes(self._h, C.byref(a), C.byref(b)))
+        return dict(deferred=a.value, literal=b.value)
 
     def grid_counters(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

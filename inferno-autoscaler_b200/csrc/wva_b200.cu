@@ -73,6 +73,9 @@ struct wva_ctx {
 
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
+    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot;
+    int grid_tail_cap = 192; int last_heavy = 0, last_slow = 0;
+    cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     int grid_r = 0, grid_b = 0; bool grid_valid = false;
     uint64_t grid_counters[3] = {0, 0, 0};
 
@@ -174,7 +177,8 @@ int wva_ctx_create(int device, wva_ctx** out) {
     ctx->device = device;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->evh0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evh1)) != cudaSuccess) {
         std::string msg = std::string("stream/event create: ") + cudaGetErrorString(e);
         delete ctx;
         return fail(nullptr, WVA_ECUDA, msg);
@@ -190,7 +194,8 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
                       &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
-                      &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->ioA, &ctx->ioB,
+                      &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
+                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->ioA, &ctx->ioB,
                       &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG};
     for (DevBuf* b : bufs) b->release();
     ctx->staging.release();
@@ -198,6 +203,8 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evk0);
     cudaEventDestroy(ctx->evk1);
+    cudaEventDestroy(ctx->evh0);
+    cudaEventDestroy(ctx->evh1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -392,15 +399,13 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     CK(cudaSetDevice(ctx->device));
     const int ns = ctx->ns, A = ctx->A;
     const size_t nPairs = (size_t)ns * A;
-    const size_t nCand = nPairs * (size_t)r_max * (size_t)b_max;
+    const size_t perPair = (size_t)r_max * (size_t)b_max;
+    const size_t nCand = nPairs * perPair;
     CK(ctx->keys.ensure((size_t)(ns ? ns : 1) * 8));
     CK(ctx->bestDev.ensure((size_t)(ns ? ns : 1) * sizeof(wva_grid_best)));
     CK(ctx->counters.ensure(3 * 8));
-    CK(ctx->gridSlowCount.ensure(4));
-    CK(ctx->faultCount.ensure(4));
-    CK(ctx->faultList.ensure((size_t)(ns ? ns : 1) * 4));
-    int slow_cap = 1 << 16;
-    CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
+    CK(ctx->gridSlowCount.ensure(8));                 // [0] literal-path count, [1] deferred count
+    CK(ctx->heavyHist.ensure(2 * 256 * 4));
     if (want_cube) {
         size_t freeB = 0, totB = 0;
         CK(cudaMemGetInfo(&freeB, &totB));
@@ -410,11 +415,24 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     }
     if (want_status) CK(ctx->status.ensure(nCand ? nCand : 1));
 
+    // The sweep runs over slices of servers so that the published service-rate tables (16 B per
+    // pair and batch size) stay within ~1 GB.
+    int srvPerSlice = ns;
+    {
+        const size_t tabPerServer = (size_t)A * b_max * sizeof(double2);
+        size_t maxSrv = ((size_t)1 << 30) / (tabPerServer ? tabPerServer : 1);
+        if (maxSrv < 1) maxSrv = 1;
+        if ((size_t)srvPerSlice > maxSrv) srvPerSlice = (int)maxSrv;
+        if (srvPerSlice < 1) srvPerSlice = 1;
+    }
+    const size_t slicePairsMax = (size_t)srvPerSlice * A;
+    CK(ctx->pairTab.ensure(slicePairsMax * (size_t)b_max * sizeof(double2)));
+
     GridParams gp;
     gp.r_max = r_max; gp.b_max = b_max;
     int n_rchunks = 1;
-    if (nPairs > 0 && nPairs < 2368) {
-        n_rchunks = (int)((2368 + nPairs - 1) / nPairs);
+    if (slicePairsMax > 0 && slicePairsMax < 2368) {
+        n_rchunks = (int)((2368 + slicePairsMax - 1) / slicePairsMax);
         if (n_rchunks > r_max) n_rchunks = r_max;
     }
     gp.r_chunk = (r_max + n_rchunks - 1) / n_rchunks;
@@ -424,70 +442,119 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     gp.status = want_status ? ctx->status.as<unsigned char>() : nullptr;
     gp.keys = ctx->keys.as<unsigned long long>();
     gp.counters = ctx->counters.as<unsigned long long>();
+    gp.pair_tab = ctx->pairTab.as<double2>();
+    gp.tail_cap = ctx->grid_tail_cap;
     gp.slow_count = ctx->gridSlowCount.as<int>();
+    gp.heavy_count = ctx->gridSlowCount.as<int>() + 1;
+
+    const size_t sliceCandMax = slicePairsMax * perPair;
+    // deferred-chain list: at most one entry per candidate of a slice, capped at 16M entries (the
+    // sweep kernel finishes a chain itself when the list is full)
+    size_t heavy_cap_sz = sliceCandMax < (size_t)(16u << 20) ? sliceCandMax : (size_t)(16u << 20);
+    if (heavy_cap_sz < 1) heavy_cap_sz = 1;
+    const int heavy_cap = (int)heavy_cap_sz;
+    CK(ctx->heavyList.ensure(heavy_cap_sz * 8));
+    CK(ctx->heavyCost.ensure(heavy_cap_sz * 4));
+    CK(ctx->heavyOrder.ensure(heavy_cap_sz * 4));
+    gp.heavy_list = ctx->heavyList.as<unsigned long long>(); gp.heavy_cost = ctx->heavyCost.as<float>();
+    gp.heavy_cap = heavy_cap;
+    int slow_cap = 1 << 16;
+    CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
 
     const size_t smem = (size_t)b_max * 20;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t nBlocks = nPairs * (size_t)gp.n_rchunks;
-    if (nBlocks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
+    if (slicePairsMax * (size_t)gp.n_rchunks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
+    CK(ctx->blockSlot.ensure((slicePairsMax * (size_t)gp.n_rchunks + 1) * sizeof(GridSlot)));
+    gp.block_slot = ctx->blockSlot.as<GridSlot>();
+    const long long stride = 11LL * b_max + 1;
 
     PhaseTimer timer(ctx, WVA_PHASE_GRID);
-    int slow = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
-        CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 4, ctx->stream));
-        if (nBlocks > 0) {
+    ctx->phase_usec[WVA_PHASE_GRID_KERNEL] = 0; ctx->phase_usec[WVA_PHASE_GRID_HEAVY] = 0;
+    ctx->last_heavy = 0; ctx->last_slow = 0;
+    CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->stream));
+    if (ns > 0) {
+        k_grid_best_init<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ns, ctx->bestDev.as<wva_grid_best>());
+        LAUNCH_CHECK();
+    }
+    for (int sBeg = 0; sBeg < ns; sBeg += srvPerSlice) {
+        const int sCnt = (ns - sBeg) < srvPerSlice ? (ns - sBeg) : srvPerSlice;
+        const size_t slicePairs = (size_t)sCnt * A;
+        const size_t nBlocks = slicePairs * (size_t)gp.n_rchunks;
+        gp.pair_base = sBeg * A;
+        int counts[2] = {0, 0};
+        int slow = 0, heavy = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
+            CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->stream));
             CK(cudaEventRecord(ctx->evk0, ctx->stream));
             k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->stream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
             CK(cudaEventRecord(ctx->evk1, ctx->stream));
+            CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            slow = counts[0]; heavy = counts[1] < heavy_cap ? counts[1] : heavy_cap;
+            {
+                float kms = 0.0f;
+                CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
+                ctx->phase_usec[WVA_PHASE_GRID_KERNEL] += (int64_t)(kms * 1000.0f + 0.5f);
+            }
+            CK(ctx->listSlot.ensure(((size_t)heavy + (size_t)(slow > slow_cap ? slow : slow_cap) + 1) * sizeof(GridSlot)));
+            gp.list_slot = ctx->listSlot.as<GridSlot>();
+            if (heavy > 0) {
+                // long chains: order by estimated length (longest first), one thread per chain
+                int* hist = ctx->heavyHist.as<int>();
+                CK(cudaEventRecord(ctx->evh0, ctx->stream));
+                CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->stream));
+                k_heavy_hist<<<(heavy + 255) / 256, 256, 0, ctx->stream>>>(gp.heavy_cost, heavy, hist);
+                LAUNCH_CHECK();
+                k_heavy_prefix<<<1, 256, 0, ctx->stream>>>(hist);
+                LAUNCH_CHECK();
+                k_heavy_scatter<<<(heavy + 255) / 256, 256, 0, ctx->stream>>>(gp.heavy_cost, heavy, hist, ctx->heavyOrder.as<int>());
+                LAUNCH_CHECK();
+                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, gp, gp.heavy_list, ctx->heavyOrder.as<int>(), heavy,
+                                                                        nullptr, 0, 0);
+                LAUNCH_CHECK();
+                CK(cudaEventRecord(ctx->evh1, ctx->stream));
+                CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                slow = counts[0];
+                float hms = 0.0f;
+                CK(cudaEventElapsedTime(&hms, ctx->evh0, ctx->evh1));
+                ctx->phase_usec[WVA_PHASE_GRID_HEAVY] += (int64_t)(hms * 1000.0f + 0.5f);
+            }
+            if (slow <= slow_cap) break;
+            slow_cap = slow;                          // rare: more literal-path candidates than the list holds
+            CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
+            // keys only ever decrease towards the true minimum: redoing the slice is safe (the work
+            // counters then count the slice twice)
         }
-        CK(cudaMemcpyAsync(&slow, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->last_heavy += heavy; ctx->last_slow += slow;
+        int listSlots = heavy;
+        if (slow > 0) {
+            size_t freeB = 0, totB = 0;
+            CK(cudaMemGetInfo(&freeB, &totB));
+            // process the literal list in pieces that fit in memory
+            size_t per = (size_t)stride * 8;
+            size_t maxItems = (freeB / 2) / per;
+            if (maxItems == 0) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
+            if (maxItems > (size_t)slow) maxItems = (size_t)slow;
+            CK(ctx->scratch.ensure(maxItems * per));
+            for (size_t done = 0; done < (size_t)slow; done += maxItems) {
+                int n = (int)(((size_t)slow - done) < maxItems ? ((size_t)slow - done) : maxItems);
+                k_grid_list<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, gp, ctx->gridSlow.as<unsigned long long>() + done, nullptr,
+                                                                   n, ctx->scratch.as<double>(), stride, heavy + (int)done);
+                LAUNCH_CHECK();
+            }
+            listSlots += slow;
+        }
+        // winners of the slice: the slot that carries a server's minimum key writes its record
         if (nBlocks > 0) {
-            float kms = 0.0f;
-            CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
-            ctx->phase_usec[WVA_PHASE_GRID_KERNEL] = (int64_t)(kms * 1000.0f + 0.5f);
-        }
-        if (slow <= slow_cap) break;
-        slow_cap = slow;                              // rare: more literal-path candidates than the list holds
-        CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
-    }
-    const long long stride = 11LL * b_max + 1;
-    if (slow > 0) {
-        size_t freeB = 0, totB = 0;
-        CK(cudaMemGetInfo(&freeB, &totB));
-        // process the literal list in slices that fit in memory
-        size_t per = (size_t)stride * 8;
-        size_t maxItems = (freeB / 2) / per;
-        if (maxItems == 0) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
-        if (maxItems > (size_t)slow) maxItems = (size_t)slow;
-        CK(ctx->scratch.ensure(maxItems * per));
-        for (size_t done = 0; done < (size_t)slow; done += maxItems) {
-            int n = (int)(((size_t)slow - done) < maxItems ? ((size_t)slow - done) : maxItems);
-            k_grid_literal<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->gridSlow.as<unsigned long long>() + done, n,
-                                                                 ctx->scratch.as<double>(), stride);
+            k_grid_claim<<<(unsigned)((nBlocks + 255) / 256), 256, 0, ctx->stream>>>(gp, gp.block_slot, (int)nBlocks, ctx->bestDev.as<wva_grid_best>());
             LAUNCH_CHECK();
         }
-    }
-    // winners
-    if (ns > 0) {
-        CK(cudaMemsetAsync(ctx->faultCount.p, 0, 4, ctx->stream));
-        k_grid_finalize<<<(ns + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->bestDev.as<wva_grid_best>(), nullptr, 0,
-                                                               nullptr, 0, ctx->faultList.as<int>(), ctx->faultCount.as<int>());
-        LAUNCH_CHECK();
-        int nf = 0;
-        CK(cudaMemcpyAsync(&nf, ctx->faultCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (nf > 0) {
-            CK(ctx->scratch.ensure((size_t)nf * (size_t)stride * 8));
-            CK(ctx->ioG.ensure((size_t)nf * 4));
-            CK(cudaMemcpyAsync(ctx->ioG.p, ctx->faultList.p, (size_t)nf * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-            k_grid_finalize<<<(nf + 63) / 64, 64, 0, ctx->stream>>>(ctx->dsys, gp, ctx->bestDev.as<wva_grid_best>(),
-                                                                   ctx->scratch.as<double>(), stride, ctx->ioG.as<int>(), nf,
-                                                                   ctx->faultList.as<int>(), ctx->faultCount.as<int>());
+        if (listSlots > 0) {
+            k_grid_claim<<<(listSlots + 255) / 256, 256, 0, ctx->stream>>>(gp, gp.list_slot, listSlots, ctx->bestDev.as<wva_grid_best>());
             LAUNCH_CHECK();
         }
     }
@@ -526,6 +593,17 @@ int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max, wva_grid_best* 
     return WVA_OK;
 }
 
+int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap) {
+    if (!ctx || tail_cap < 0) return WVA_EINVAL;
+    ctx->grid_tail_cap = tail_cap;
+    return WVA_OK;
+}
+int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal) {
+    if (!ctx) return WVA_EINVAL;
+    if (deferred) *deferred = ctx->last_heavy;
+    if (literal) *literal = ctx->last_slow;
+    return WVA_OK;
+}
 int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic, uint64_t* candidates_ok) {
     if (!ctx) return WVA_EINVAL;
     if (steps_executed) *steps_executed = ctx->grid_counters[0];

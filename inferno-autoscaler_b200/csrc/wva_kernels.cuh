@@ -3,7 +3,8 @@
 //   k_pairs          one thread per (server, accelerator): core.CreateAllocation + penalty
 //   k_grid           candidate sweep: one thread per (server, accel, replicas, batch) candidate,
 //                    service-rate tables staged in shared memory, warp-shuffle + block argmin
-//   k_grid_finalize  decode the per-server winners
+//   k_grid_list      deferred long chains / materialised-p[] chains, one thread per candidate
+//   k_grid_claim     per-server winners from the published (key, metrics) slots
 //   k_solve_unlimited / k_greedy_*   the assignment step
 //   k_totals         System.AllocateByType partial sums (input of the one NCCL allreduce)
 //   k_queue_analyze / k_queue_size   the pkg/analyzer public API, batched
@@ -240,15 +241,24 @@ __global__ void k_pair_bucket_scatter(const long long* __restrict__ nIn, int nPa
 // Candidate sweep
 // ---------------------------------------------------------------------------------------
 
+// best candidate of a block / a list thread: key + the metrics a wva_grid_best needs
+struct GridSlot { unsigned long long key; float cost, itl, ttft, rho; int sl; int pad; };
+
 struct GridParams {
     int r_max, b_max;
     int r_chunk, n_rchunks;          // replicas per block / blocks per pair
     int s0, ns;                      // shard
+    int pair_base;                   // (server, accelerator) pairs of the shard that precede the slice being swept
     wva_metrics* cube;               // [ns*A*r_max*b_max] or nullptr
     unsigned char* status;           // same extent or nullptr
     unsigned long long* keys;        // [ns] per-server argmin key (initialised to ~0)
     unsigned long long* counters;    // [0] steps executed, [1] algorithmic steps, [2] candidates analysed ok
     unsigned long long* slow_list; int* slow_count; int slow_cap;   // candidate ids (relative to shard) needing the literal path
+    double2* pair_tab;               // [ns*A][b_max] {rate, refined reciprocal}: written by k_grid, read by the list kernel
+    struct GridSlot* block_slot;     // [blocks of k_grid] best candidate of each block with its metrics
+    struct GridSlot* list_slot;      // [heavy_cap + slow_cap] one per list-kernel thread
+    int tail_cap;                    // tail steps a candidate may take inside k_grid before it is deferred
+    unsigned long long* heavy_list; float* heavy_cost; int* heavy_count; int heavy_cap;   // deferred (long) chains
 };
 
 // order-preserving map float -> uint32 (ascending), -0 canonicalised by the caller
@@ -285,7 +295,8 @@ struct GridServer {
 // MaxQueueSize 10 b, service rates from the shared-memory table.  A fresh model has p[0] = 0 so
 // the validity test (queuemodel.go:30-31) sees rho = 1: valid iff 1 < K and lambda >= 0.
 __device__ __forceinline__ int analyze_table(const ServTable& tb, const GridServer& gs, int b, float rate, bool tame,
-                                             wva_metrics& m, float& rateTPS, unsigned long long& steps) {
+                                             int tailCap, wva_metrics& m, float& rateTPS, unsigned long long& steps,
+                                             float& deferCost) {
     const int K = b * WVA_MAX_QUEUE_TO_BATCH_RATIO + b;
     const float lambdaMax = tb.rateF[b - 1] * (1.0f - WVA_EPSILON);
     const float rateMax = lambdaMax * 1000.0f;
@@ -296,7 +307,11 @@ __device__ __forceinline__ int analyze_table(const ServTable& tb, const GridServ
     const float lambda = rate / 1000.0f;
     if ((1.0f >= (float)K) || (lambda < 0.0f)) return WVA_CAND_ERR_MODEL;
     SolveStats st;
-    if (solve_stream_table(tb, b, K, lambda, tame, st, steps) != WVA_SOLVE_OK) return -1;   // literal path
+    ProvTable pv; pv.rateD = tb.rateD; pv.rcp = tb.rcp; pv.rateF_ = tb.rateF;
+    int rc = solve_fast(pv, b, K, lambda, tame, tailCap, st, steps, deferCost);
+    if (rc == WVA_SOLVE_DEFER) return -2;                                 // long chain: heavy kernel
+    if (rc == WVA_SOLVE_CAREFUL) rc = solve_stream_table(tb, b, K, lambda, tame, st, steps);
+    if (rc != WVA_SOLVE_OK) return -1;                                    // literal path
     float effConc = effective_concurrency(st.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
     float rho = st.avgNumInServers / (float)b;
     rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
@@ -344,8 +359,9 @@ __device__ __forceinline__ void load_grid_server(const DevSystem& sys, int s, in
 // table (float, double and refined reciprocal, 20 B per batch size) is built once into shared
 // memory; warps then pull (replicas, 32 consecutive batch sizes) work items from a shared counter:
 // lanes of a warp share lambda and differ only by batch size, so their trip counts are close.
+// Chains whose tail outlasts gp.tail_cap are deferred to k_grid_list.
 #define WVA_GRID_THREADS 256
-__global__ void __launch_bounds__(WVA_GRID_THREADS)
+__global__ void __launch_bounds__(WVA_GRID_THREADS, 3)
 k_grid(DevSystem sys, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* rateD = reinterpret_cast<double*>(smem_raw);
@@ -355,7 +371,8 @@ k_grid(DevSystem sys, GridParams gp) {
     __shared__ unsigned long long sh_key;
     __shared__ unsigned long long sh_cnt[3];
 
-    const int pairLocal = blockIdx.x / gp.n_rchunks;       // (s - s0) * A + a
+    const int pairSlice = blockIdx.x / gp.n_rchunks;       // pair index inside the slice
+    const int pairLocal = gp.pair_base + pairSlice;        // (s - s0) * A + a
     const int rchunk = blockIdx.x % gp.n_rchunks;
     const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
     const int s = gp.s0 + sl;
@@ -364,7 +381,10 @@ k_grid(DevSystem sys, GridParams gp) {
     const int B = gp.b_max;
     const int lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) { sh_item = 0; sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; }
+    if (threadIdx.x == 0) {
+        sh_item = 0; sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
+        gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
+    }
 
     const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
     GridServer gs;
@@ -390,14 +410,17 @@ k_grid(DevSystem sys, GridParams gp) {
     }
     __syncthreads();
 
-    // ---- stage the service-rate table -------------------------------------------------
+    // ---- stage the service-rate table (and publish it for the deferred-chain kernel) ------------
     ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
+    double2* gtab = (rchunk == 0) ? gp.pair_tab + (size_t)pairSlice * B : nullptr;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         float r = sf.rate(i + 1);
         rateF[i] = r;
         double d = (double)r;
+        double y = rcp_refined(d);
         rateD[i] = d;
-        rcp[i] = rcp_refined(d);
+        rcp[i] = y;
+        if (gtab) gtab[i] = make_double2(d, y);
         if (!(r > 0.0f) || !(r < CUDART_INF_F)) atomicMin(&sh_nGood, i);
     }
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
@@ -409,6 +432,7 @@ k_grid(DevSystem sys, GridParams gp) {
     const int bChunks = (B + 31) / 32;
     const int nItems = (r_hi - r_lo + 1) * bChunks;
     unsigned long long bestKey = WVA_KEY_NONE;
+    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
     unsigned long long steps = 0, algSteps = 0, okCount = 0;
     for (;;) {
         int item;
@@ -428,10 +452,21 @@ k_grid(DevSystem sys, GridParams gp) {
         float rateTPS = 0.0f;
         int st;
         bool feasible = false;
+        float deferCost = 0.0f;
+        bool deferred = false;
         if (b > nGood) st = -1;
-        else st = analyze_table(tb, gs, b, rate, tame, m, rateTPS, steps);
+        else {
+            // one call site: the second trip (cap 0) only happens when the deferred list is full
+            for (int cap = gp.tail_cap;; cap = 0) {
+                st = analyze_table(tb, gs, b, rate, tame, cap, m, rateTPS, steps, deferCost);
+                if (st != -2) break;
+                int k = atomicAdd(gp.heavy_count, 1);
+                if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)ci; gp.heavy_cost[k] = deferCost; deferred = true; break; }
+            }
+        }
+        if (deferred) continue;      // long chain: k_grid_list groups chains of similar length
         if (st == -1) {
-            // literal path: queue the candidate, leave outputs to k_grid_literal
+            // literal path: queue the candidate, outputs come from k_grid_list
             int k = atomicAdd(gp.slow_count, 1);
             if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
             continue;
@@ -440,7 +475,9 @@ k_grid(DevSystem sys, GridParams gp) {
             okCount++;
             algSteps += 2ULL * (unsigned long long)(11 * b + 1);
             unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
-            if (key < bestKey) bestKey = key;
+            if (key < bestKey) {
+                bestKey = key; bestItl = m.avg_token_time; bestTtft = m.avg_wait_time + m.avg_prefill_time; bestRho = m.rho;
+            }
         } else {
             m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
             m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
@@ -453,32 +490,43 @@ k_grid(DevSystem sys, GridParams gp) {
         if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
     }
 
-    // ---- warp-shuffle then block argmin, one global atomic per block ----------------------
+    // ---- warp-shuffle then block argmin; the owner of the block minimum publishes its metrics ----
+    unsigned long long warpKey = bestKey;
     for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_down_sync(0xffffffffu, bestKey, o);
-        if (other < bestKey) bestKey = other;
+        unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
+        if (other < warpKey) warpKey = other;
         steps += __shfl_down_sync(0xffffffffu, steps, o);
         algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
         okCount += __shfl_down_sync(0xffffffffu, okCount, o);
     }
     if (lane == 0) {
-        if (bestKey != WVA_KEY_NONE) atomicMin(&sh_key, bestKey);
+        if (warpKey != WVA_KEY_NONE) atomicMin(&sh_key, warpKey);
         atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
     }
     __syncthreads();
+    const unsigned long long blockKey = sh_key;
+    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {          // keys are unique per candidate: one owner
+        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
+        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
+        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        gp.block_slot[blockIdx.x] = sl_;
+        atomicMin(&gp.keys[sl], blockKey);
+    }
     if (threadIdx.x == 0) {
-        if (sh_key != WVA_KEY_NONE) atomicMin(&gp.keys[sl], sh_key);
         atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
     }
 }
 
-// Candidate evaluated through the formula-based analyzer (streaming, or literal when scratch != 0).
-// Same arithmetic as analyze_table, hence the same bits.
-__device__ int analyze_candidate(const DevSystem& sys, int s, int a, int r, int b, double* scratch, GridServer& gs,
-                                 wva_metrics& m, float& rate, float& rateTPS, int& fault, unsigned long long& steps) {
+// Candidate evaluated through the formula-based analyzer.  Same arithmetic as analyze_table, hence
+// the same bits.  tab: the pair's published {rate, reciprocal} table (unified-loop streaming solver)
+// or nullptr; scratch: p[] for the literal path or nullptr.
+__device__ int analyze_candidate(const DevSystem& sys, int s, int a, int r, int b, const double2* tab, double* scratch,
+                                 GridServer& gs, wva_metrics& m, float& rate, float& rateTPS, int& fault,
+                                 unsigned long long& steps) {
     load_grid_server(sys, s, a, gs);
     Analyzer qa;
     qa.build(gs.sp, b, (long long)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, gs.inTok, gs.outTok, scratch);
+    qa.tab = tab; qa.uni = true;
     const float lamMaxBack = qa.rateMax / 1000.0f;
     rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
     rate = gs.totalRate / (float)r;
@@ -488,67 +536,113 @@ __device__ int analyze_candidate(const DevSystem& sys, int s, int a, int r, int 
     return st;
 }
 
-// literal path for the candidates k_grid queued
-__global__ void __launch_bounds__(64)
-k_grid_literal(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, int nList, double* scratch, long long stride) {
+// Candidates from a list, one thread each.
+//   scratch == nullptr : the deferred long chains (streaming, unified-loop solver on the published
+//                        tables); `order` sorts them by estimated length so that the lanes of a warp
+//                        finish together; a chain that needs the materialised path is appended to
+//                        the literal list.
+//   scratch != nullptr : the literal list (p[] materialised, `stride` doubles per thread).
+// Each thread publishes key + metrics in gp.list_slot[slot_base + t] for k_grid_claim.
+__global__ void __launch_bounds__(128)
+k_grid_list(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, const int* __restrict__ order,
+            int nList, double* scratch, long long stride, int slot_base) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nList) return;
-    const size_t ci = (size_t)list[t];
-    const int B = gp.b_max;
-    const int b = (int)(ci % B) + 1;
-    const int r = (int)((ci / B) % gp.r_max) + 1;
-    const int pairLocal = (int)(ci / ((size_t)B * gp.r_max));
-    const int sl = pairLocal / sys.A, a = pairLocal % sys.A, s = gp.s0 + sl;
-    GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0; unsigned long long steps = 0;
-    int st = analyze_candidate(sys, s, a, r, b, scratch + (size_t)t * stride, gs, m, rate, rateTPS, fault, steps);
-    bool feasible = false;
-    if (st == WVA_CAND_OK) {
-        unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
-        if (key != WVA_KEY_NONE) atomicMin(&gp.keys[sl], key);
-        atomicAdd(&gp.counters[1], 2ULL * (unsigned long long)(11 * b + 1));
-        atomicAdd(&gp.counters[2], 1ULL);
-    } else {
-        m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
-        m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+    unsigned long long steps = 0, alg = 0, okc = 0;
+    if (t < nList) {
+        const size_t ci = (size_t)list[order ? order[t] : t];
+        const int B = gp.b_max;
+        const int b = (int)(ci % B) + 1;
+        const int r = (int)((ci / B) % gp.r_max) + 1;
+        const int pairLocal = (int)(ci / ((size_t)B * gp.r_max));
+        const int sl = pairLocal / sys.A, a = pairLocal % sys.A, s = gp.s0 + sl;
+        GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0;
+        GridSlot slot; slot.key = WVA_KEY_NONE; slot.cost = slot.itl = slot.ttft = slot.rho = 0.0f; slot.sl = sl; slot.pad = 0;
+        int st = analyze_candidate(sys, s, a, r, b, scratch ? nullptr : gp.pair_tab + (size_t)(pairLocal - gp.pair_base) * B,
+                                   scratch ? scratch + (size_t)t * stride : nullptr, gs, m, rate, rateTPS, fault, steps);
+        if (fault == 1) {
+            int k = atomicAdd(gp.slow_count, 1);
+            if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+        } else {
+            bool feasible = false;
+            if (st == WVA_CAND_OK) {
+                unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
+                if (key != WVA_KEY_NONE) {
+                    slot.key = key; slot.itl = m.avg_token_time; slot.ttft = m.avg_wait_time + m.avg_prefill_time;
+                    slot.rho = m.rho; slot.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+                    if (key < gp.keys[sl]) atomicMin(&gp.keys[sl], key);
+                }
+                alg = 2ULL * (unsigned long long)(11 * b + 1);
+                okc = 1;
+            } else {
+                m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            }
+            if (gp.cube) {
+                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+            }
+            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+        }
+        gp.list_slot[slot_base + t] = slot;
     }
-    atomicAdd(&gp.counters[0], steps);
-    if (gp.cube) gp.cube[ci] = m;
-    if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        alg += __shfl_down_sync(0xffffffffu, alg, o);
+        okc += __shfl_down_sync(0xffffffffu, okc, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd(&gp.counters[0], steps);
+        if (alg) atomicAdd(&gp.counters[1], alg);
+        if (okc) atomicAdd(&gp.counters[2], okc);
+    }
 }
 
-// decode per-server winners; metrics of the winner are re-evaluated (one Analyze per server).
-// First pass: list == nullptr, one thread per shard server, streaming solver; servers whose winner
-// needs the materialised path are appended to fault_list.  Second pass: list = those servers,
-// scratch = nList * stride doubles.
-__global__ void __launch_bounds__(64)
-k_grid_finalize(DevSystem sys, GridParams gp, wva_grid_best* __restrict__ best, double* scratch, long long stride,
-                const int* __restrict__ list, int nList, int* __restrict__ fault_list, int* fault_count) {
+// ---- ordering of the deferred chains by estimated length (256 buckets, longest first) --------
+__device__ __forceinline__ int heavy_bucket(float cost) {
+    int k = (int)(__float_as_uint(cost < 1.0f ? 1.0f : cost) >> 19) - (127 << 4);    // 16 buckets per octave
+    k = k < 0 ? 0 : (k > 255 ? 255 : k);
+    return 255 - k;
+}
+__global__ void k_heavy_hist(const float* __restrict__ cost, int n, int* __restrict__ hist) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int sl;
-    if (list) { if (t >= nList) return; sl = list[t]; }
-    else { if (t >= gp.ns) return; sl = t; }
+    if (t < n) atomicAdd(&hist[heavy_bucket(cost[t])], 1);
+}
+__global__ void k_heavy_prefix(int* hist /*[256] -> exclusive prefix in place*/) {
+    __shared__ int sh[256];
+    int t = threadIdx.x;
+    sh[t] = hist[t];
+    __syncthreads();
+    if (t == 0) { int run = 0; for (int i = 0; i < 256; ++i) { int c = sh[i]; sh[i] = run; run += c; } }
+    __syncthreads();
+    hist[t] = sh[t];
+}
+__global__ void k_heavy_scatter(const float* __restrict__ cost, int n, int* __restrict__ cursor, int* __restrict__ order) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) order[atomicAdd(&cursor[heavy_bucket(cost[t])], 1)] = t;
+}
+
+// Per-server winners: keys[] holds the minimum key of every server; the slot that carries that key
+// (exactly one: keys are unique per candidate) writes the wva_grid_best record.  No re-evaluation.
+__global__ void k_grid_best_init(int ns, wva_grid_best* __restrict__ best) {
+    int sl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= ns) return;
     wva_grid_best out;
     out.acc = -1; out.replicas = 0; out.batch = 0; out.cost = out.value = out.itl = out.ttft = out.rho = 0.0f;
-    const unsigned long long key = gp.keys[sl];
-    if (key != WVA_KEY_NONE) {
-        const int a = (int)((key >> 24) & 0xff), r = (int)((key >> 14) & 0x3ff) + 1, b = (int)(key & 0x3fff) + 1;
-        GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0; unsigned long long steps = 0;
-        int st = analyze_candidate(sys, gp.s0 + sl, a, r, b, list ? scratch + (size_t)t * stride : nullptr, gs, m,
-                                   rate, rateTPS, fault, steps);
-        if (fault == 1) {                      // winner needs the literal path: host re-runs with scratch
-            fault_list[atomicAdd(fault_count, 1)] = sl;
-            return;
-        }
-        if (st == WVA_CAND_OK) {
-            out.acc = a; out.replicas = r; out.batch = b;
-            out.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
-            out.value = unsortable_f32((unsigned)(key >> 32));
-            out.itl = m.avg_token_time;
-            out.ttft = m.avg_wait_time + m.avg_prefill_time;
-            out.rho = m.rho;
-        }
-    }
     best[sl] = out;
+}
+__global__ void k_grid_claim(GridParams gp, const GridSlot* __restrict__ slots, int nSlots, wva_grid_best* __restrict__ best) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nSlots) return;
+    const GridSlot sl_ = slots[t];
+    if (sl_.key == WVA_KEY_NONE) return;
+    if (gp.keys[sl_.sl] != sl_.key) return;
+    wva_grid_best out;
+    out.acc = (int)((sl_.key >> 24) & 0xff); out.replicas = (int)((sl_.key >> 14) & 0x3ff) + 1; out.batch = (int)(sl_.key & 0x3fff) + 1;
+    out.cost = sl_.cost;
+    out.value = unsortable_f32((unsigned)(sl_.key >> 32));
+    out.itl = sl_.itl; out.ttft = sl_.ttft; out.rho = sl_.rho;
+    best[sl_.sl] = out;
 }
 
 // ---------------------------------------------------------------------------------------

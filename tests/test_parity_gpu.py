@@ -210,7 +210,7 @@ def test_solve_greedy_ties(wva, oracle, ctx):
     img.srv_arrival_rpm[:] = 900.0; img.srv_keep_acc[:] = 0; img.srv_cur_acc[:] = -1; img.srv_cur_cost[:] = 0
     img.srv_cur_replicas[:] = 0; img.srv_max_batch[:] = 32; img.srv_slo_tps[:] = 0
     pairs, feas, _ = oracle.analyze_pairs(img)
-    assert feas.all()
+    assert feas.reshape(img.S, img.A).any(axis=1).all() and feas.sum() >= 2 * img.S
     acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
     wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.45)
     for policy in (0, 1, 3):
