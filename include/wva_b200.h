@@ -224,6 +224,10 @@ int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best);
  * wva_pairs_commit so that wva_solve may run the (sequential, replicated) greedy assignment. */
 int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
 int wva_pairs_commit(wva_ctx* ctx);
+/* Tuning: shards with at most max_pairs (server, accelerator) pairs use the warp-per-pair kernel
+ * (speculative bisection, lowest latency); larger shards use one thread per pair (highest
+ * throughput).  Results do not depend on it.  Default 16384; 0 = always thread-per-pair. */
+int wva_pairs_set_warp_max(wva_ctx* ctx, int32_t max_pairs);
 /* Chain-state updates executed by the last wva_analyze_pairs (instrumentation). */
 int wva_pair_steps(wva_ctx* ctx, uint64_t* steps);
 

@@ -64,7 +64,8 @@ struct wva_ctx {
     // pair results (full S*A extent; a rank fills its shard rows)
     DevBuf pairBuf; DevAllocs pairs{}; unsigned char* feasible = nullptr;
     bool pairs_valid = false; bool pairs_complete = false;
-    DevBuf pairN, pairOrder, pairHist, slowList, slowCount, stepCounter, scratch, scratchOff;
+    DevBuf pairN, pairOrder, pairHist, slowList, slowCount, stepCounter, scratch, scratchOff, pairTabs, pairTabOff;
+    int pairs_warp_max = 16384;
 
     // solution
     DevBuf chosenBuf; DevAllocs chosen{}; int* chosen_acc = nullptr; bool solved = false;
@@ -192,7 +193,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
-                      &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->chosenBuf, &ctx->totals,
+                      &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
                       &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->ioA, &ctx->ioB,
@@ -299,6 +300,28 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
     if (nPairs > 0) {
         k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
         LAUNCH_CHECK();
+        if (nPairs <= ctx->pairs_warp_max) {
+            // latency-oriented variant: one warp per pair, per-pair {rate, reciprocal} tables in HBM
+            std::vector<long long> nHost((size_t)nPairs), offs((size_t)nPairs);
+            CK(cudaMemcpyAsync(nHost.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            long long total = 0;
+            const long long budget = (2LL << 30) / 16;          // at most 2 GB of tables
+            for (int i = 0; i < nPairs; ++i) {
+                long long N = nHost[(size_t)i];
+                if (N <= 0) { offs[(size_t)i] = 0; continue; }   // pair does no queueing work: offset unused
+                if (N > (1LL << 26) || total + N > budget) { offs[(size_t)i] = -1; continue; }
+                offs[(size_t)i] = total; total += N;
+            }
+            CK(ctx->pairTabs.ensure((size_t)(total ? total : 1) * 16));
+            CK(ctx->pairTabOff.ensure((size_t)nPairs * 8));
+            CK(cudaMemcpyAsync(ctx->pairTabOff.p, offs.data(), (size_t)nPairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+            const int warpsPerBlock = WVA_PAIRS_WARP_THREADS / 32;
+            k_pairs_warp<<<(nPairs + warpsPerBlock - 1) / warpsPerBlock, WVA_PAIRS_WARP_THREADS, 0, ctx->stream>>>(
+                ctx->dsys, ctx->s0, nPairs, ctx->pairTabOff.as<long long>(), ctx->pairTabs.as<double2>(), ctx->pairs, ctx->feasible,
+                ctx->slowList.as<int>(), ctx->slowCount.as<int>(), ctx->stepCounter.as<unsigned long long>());
+            LAUNCH_CHECK();
+        } else {
         const int* order = nullptr;
         if (nPairs > 1024) {
             // order pairs by chain length (bucket = bit length of N, heaviest first) so that the lanes
@@ -324,6 +347,7 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
                                                               ctx->slowList.as<int>(), ctx->slowCount.as<int>(),
                                                               ctx->stepCounter.as<unsigned long long>());
         LAUNCH_CHECK();
+        }
         CK(cudaMemcpyAsync(&slow, ctx->slowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -381,6 +405,11 @@ int wva_pairs_commit(wva_ctx* ctx) {
     if (!ctx) return WVA_EINVAL;
     if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "analyze_pairs has not run");
     ctx->pairs_complete = true;
+    return WVA_OK;
+}
+int wva_pairs_set_warp_max(wva_ctx* ctx, int32_t max_pairs) {
+    if (!ctx || max_pairs < 0) return WVA_EINVAL;
+    ctx->pairs_warp_max = max_pairs;
     return WVA_OK;
 }
 int wva_pair_steps(wva_ctx* ctx, uint64_t* steps) {

@@ -212,6 +212,290 @@ k_pairs_literal(DevSystem sys, int s0, const int* __restrict__ list, int nList, 
     atomicAdd(step_counter, steps);
 }
 
+// ---------------------------------------------------------------------------------------
+// k_pairs_warp: one WARP per (server, accelerator) pair — the latency-oriented variant used when
+// there are fewer pairs than the GPU has warps.  core.CreateAllocation is a chain of ~25-205
+// dependent Solves (two bisections, then two Analyzes); a single thread runs them one after the
+// other.  Here:
+//   * the pair's {service rate, refined reciprocal} table is built once by the 32 lanes into global
+//     memory (N x 16 B), so every chain step, ramp included, is DMUL + DMUL + 2 DFMA;
+//   * the TTFT and ITL bisections of QueueAnalyzer.Size run concurrently on the two half-warps
+//     (they only share the model through the stale-rho validity test, which is vacuous for
+//     K = 11N >= 11 and lambda >= 0: SURVEY Appendix D.3);
+//   * each bisection is evaluated speculatively: the interval endpoints are known float32 values, so
+//     the midpoints of the next 4 levels of the bisection tree (15 nodes) are known too; 15 lanes
+//     evaluate them at once and the warp then walks the tree with the reference's own comparisons.
+//     The sequence of midpoints, iteration count (<= 100) and early exits are exactly those of
+//     analyzer.BinarySearch (utils.go:26-70); evaluations off the realised path are discarded;
+//   * the two trailing Analyzes (queueanalyzer.go:237-241, allocation.go:148) run side by side: the
+//     second one's rate depends on the first one's throughput, which equals lambda*1000 exactly
+//     whenever float32(p[K]) < 2^-25 — it is evaluated under that guess and re-done if wrong.
+// Lanes call solve_uni together (idle lanes pass active = false), so the passes stay converged.
+// ---------------------------------------------------------------------------------------
+
+// x of node `node` (1-based heap index; children 2j = "xMax = x", 2j+1 = "xMin = x") of the
+// bisection tree over [lo, hi]
+__device__ __forceinline__ float bisect_node_x(float lo, float hi, int node) {
+    const int depth = 31 - __clz(node);
+    float x = 0.5f * (lo + hi);
+    for (int l = depth - 1; l >= 0; --l) {
+        if ((node >> l) & 1) lo = x; else hi = x;
+        x = 0.5f * (lo + hi);
+    }
+    return x;
+}
+
+struct WarpPair {
+    ServFormula sv; ProvTableF pv;
+    int N, K; long long inTok, outTok; bool tame;
+    float rateMin, rateMax;
+};
+
+// one evaluation per lane (EvalTTFT / EvalITL / Analyze share the Solve); returns false when the
+// lane's chain needs the materialised path
+__device__ __forceinline__ bool warp_solve(const WarpPair& wp, bool active, float x, SolveStats& st, unsigned long long& steps,
+                                           bool& valid) {
+    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active);
+    valid = true;
+    if (!active) return true;
+    if (x < 0.0f) { valid = false; return true; }                       // queuemodel.go:31 (stale rho is in [0,1] < K)
+    if (rc == WVA_SOLVE_CAREFUL) rc = solve_stream(wp.sv, (long long)wp.N, (long long)wp.K, x, wp.tame, st, steps);
+    return rc == WVA_SOLVE_OK;
+}
+__device__ __forceinline__ float eval_y(const WarpPair& wp, int kind, const SolveStats& st) {
+    float effConc = effective_concurrency(st.avgServTime, wp.sv.sp, wp.inTok, wp.outTok, wp.N);
+    if (kind == 0) return st.avgWaitTime + prefill_time(wp.sv.sp, wp.inTok, effConc);   // EvalTTFT :270-279
+    return decode_time(wp.sv.sp, effConc);                                              // EvalITL  :283-290
+}
+// QueueAnalyzer.Analyze's metrics from a Solve (queueanalyzer.go:152-173)
+__device__ __forceinline__ void metrics_from(const WarpPair& wp, const SolveStats& st, wva_metrics& m) {
+    float effConc = effective_concurrency(st.avgServTime, wp.sv.sp, wp.inTok, wp.outTok, wp.N);
+    float rho = st.avgNumInServers / (float)wp.N;
+    rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+    m.throughput = st.throughput * 1000.0f;
+    m.avg_resp_time = st.avgRespTime;
+    m.avg_wait_time = st.avgWaitTime;
+    m.avg_num_in_serv = st.avgNumInServers;
+    m.avg_prefill_time = prefill_time(wp.sv.sp, wp.inTok, effConc);
+    m.avg_token_time = decode_time(wp.sv.sp, effConc);
+    m.max_rate = wp.rateMax;
+    m.rho = rho;
+}
+__device__ __forceinline__ SolveStats shfl_stats(const SolveStats& s, int src) {
+    SolveStats o;
+    o.rho = __shfl_sync(0xffffffffu, s.rho, src);
+    o.avgNumInServers = __shfl_sync(0xffffffffu, s.avgNumInServers, src);
+    o.avgNumInSystem = __shfl_sync(0xffffffffu, s.avgNumInSystem, src);
+    o.throughput = __shfl_sync(0xffffffffu, s.throughput, src);
+    o.avgRespTime = __shfl_sync(0xffffffffu, s.avgRespTime, src);
+    o.avgServTime = __shfl_sync(0xffffffffu, s.avgServTime, src);
+    o.avgWaitTime = __shfl_sync(0xffffffffu, s.avgWaitTime, src);
+    return o;
+}
+
+#define WVA_PAIRS_WARP_THREADS 128
+__global__ void __launch_bounds__(WVA_PAIRS_WARP_THREADS)
+k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ tabOff, double2* tabs, DevAllocs out,
+             unsigned char* feasible, int* slow_list, int* slow_count, unsigned long long* step_counter) {
+    const int pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp-uniform
+    const int lane = threadIdx.x & 31;
+    if (pid >= nPairs) return;
+    const int s = s0 + pid / sys.A, a = pid % sys.A;
+    const size_t gi = (size_t)s * sys.A + a;
+    unsigned long long steps = 0;
+    AllocRec rec = empty_alloc();
+    bool ok = false;          // CreateAllocation != nil
+    bool toSlow = false;      // needs the materialised path (whole pair re-done by k_pairs_literal)
+
+    // every lane runs the scalar part redundantly (uniform control flow)
+    do {
+        if (!is_candidate_accel(sys, s, a) || !pair_lookups_ok(sys, s, a)) break;
+        const float arrival = sys.srv_arrival_rpm[s];
+        const long long inTok = sys.srv_in_tokens[s], outTok = sys.srv_out_tokens[s];
+        if (arrival == 0.0f || outTok == 0) { rec = zero_load_allocation(sys, s, a); ok = true; break; }
+        const int m = sys.srv_model[s];
+        const size_t pi = (size_t)m * sys.A + a;
+        const long long Kt = outTok;
+        long long N;
+        if (sys.srv_max_batch[s] > 0) N = sys.srv_max_batch[s];
+        else { N = go_divi(go_muli(sys.perf_max_batch[pi], sys.perf_at_tokens[pi]), Kt); if (N < 1) N = 1; }
+        const long long maxQueue = go_muli(N, WVA_MAX_QUEUE_TO_BATCH_RATIO);
+        if (!config_ok(N, maxQueue, inTok, Kt)) break;
+        if (tabOff[pid] < 0 || N > (1LL << 26)) { toSlow = true; break; }   // no table budget: thread kernel handles it
+        WarpPair wp;
+        ServiceParms sp; sp.alpha = sys.perf_alpha[pi]; sp.beta = sys.perf_beta[pi];
+        sp.gamma = sys.perf_gamma[pi]; sp.delta = sys.perf_delta[pi];
+        wp.sv.init(sp, inTok, Kt);
+        wp.N = (int)N; wp.K = (int)(maxQueue + N); wp.inTok = inTok; wp.outTok = Kt;
+        wp.tame = tame_parms(sp, inTok, Kt);
+        double2* tab = tabs + tabOff[pid];
+        // BuildModel (queueanalyzer.go:99-131): the table, cooperatively
+        bool bad = false;
+        for (int i = lane; i < wp.N; i += 32) {
+            float r = wp.sv.rate(i + 1);
+            if (!(r > 0.0f) || !(r < CUDART_INF_F)) bad = true;
+            double d = (double)r;
+            tab[i] = make_double2(d, rcp_refined(d));
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, bad)) { toSlow = true; break; }
+        wp.pv.tab = tab; wp.pv.sf = &wp.sv;
+        {
+            float lambdaMin = wp.sv.rate(1) * WVA_EPSILON;
+            float lambdaMax = wp.sv.rate(wp.N) * (1.0f - WVA_EPSILON);
+            wp.rateMin = lambdaMin * 1000.0f; wp.rateMax = lambdaMax * 1000.0f;
+        }
+        const float tTTFT = sys.srv_slo_ttft[s], tITL = sys.srv_slo_itl[s], tTPS = sys.srv_slo_tps[s];
+        // ---- QueueAnalyzer.Size (queueanalyzer.go:185-255) ------------------------------------
+        if (tITL < 0.0f || tTTFT < 0.0f || tTPS < 0.0f) break;
+        const float lambdaMin = wp.rateMin / 1000.0f, lambdaMax = wp.rateMax / 1000.0f;
+        const int half = lane >> 4, hl = lane & 15, base = lane & 16;
+        const float target = half == 0 ? tTTFT : tITL;
+        const bool searching = target > 0.0f;          // this half-warp's bisection is requested
+        float lo = lambdaMin, hi = lambdaMax;
+        float xStar = lambdaMax;                       // lambdaStar when the target is disabled
+        int ind = 0, iters = 0;
+        bool done = !searching, failed = false, inc = false;
+        if (searching && lambdaMin > lambdaMax) { failed = true; done = true; }     // utils.go:29-31
+        SolveStats st; st.rho = st.avgNumInServers = st.avgNumInSystem = st.throughput = st.avgRespTime = st.avgServTime = st.avgWaitTime = 0.0f;
+        float lastX = -1.0f;                           // this lane's most recent evaluation point
+        bool first = true;
+        while (__any_sync(0xffffffffu, !done)) {
+            // --- choose this lane's evaluation point ---
+            int node = 0; bool act = false; float x = 0.0f;
+            if (!done) {
+                if (first) {
+                    if (hl == 0) { act = true; x = lo; }
+                    else if (hl == 1) { act = true; x = hi; }
+                    else if (hl <= 8) { node = hl - 1; act = true; x = bisect_node_x(lo, hi, node); }
+                } else if (hl >= 1) { node = hl; act = true; x = bisect_node_x(lo, hi, node); }
+                // never evaluate beyond the reference's iteration budget
+                if (node > 0 && (31 - __clz(node)) >= WVA_BISECT_MAXIT - iters) act = false;
+            }
+            bool valid;
+            bool solved = warp_solve(wp, act, x, st, steps, valid);
+            if (act) lastX = x;
+            if (__any_sync(0xffffffffu, act && !solved)) { toSlow = true; break; }
+            const float y = act && valid ? eval_y(wp, half, st) : 0.0f;
+            // --- walk the realised path (uniform inside each half-warp) ---
+            if (first) {
+                const float yb0 = __shfl_sync(0xffffffffu, y, base + 0), yb1 = __shfl_sync(0xffffffffu, y, base + 1);
+                const bool v0 = __shfl_sync(0xffffffffu, (int)valid, base + 0), v1 = __shfl_sync(0xffffffffu, (int)valid, base + 1);
+                if (!done) {
+                    if (!v0) { failed = true; done = true; }
+                    else if (within_tolerance(yb0, target, WVA_BISECT_TOL)) { xStar = lo; ind = 0; done = true; }
+                    else if (!v1) { failed = true; done = true; }
+                    else if (within_tolerance(yb1, target, WVA_BISECT_TOL)) { xStar = hi; ind = 0; done = true; }
+                    else {
+                        inc = yb0 < yb1;
+                        if ((inc && target < yb0) || (!inc && target > yb0)) { xStar = lo; ind = -1; done = true; }
+                        else if ((inc && target > yb1) || (!inc && target < yb1)) { xStar = hi; ind = +1; done = true; }
+                    }
+                }
+            }
+            {
+                const int levels = first ? 3 : 4;
+                int cur = 1;
+                for (int l = 0; l < levels; ++l) {
+                    const int src = base + (first ? cur + 1 : cur);
+                    const float ys = __shfl_sync(0xffffffffu, y, src);
+                    const bool vs = __shfl_sync(0xffffffffu, (int)valid, src);
+                    if (!done) {
+                        if (iters == WVA_BISECT_MAXIT) { done = true; }
+                        else {
+                            const float xs = 0.5f * (lo + hi);
+                            ++iters;
+                            if (!vs) { failed = true; done = true; }
+                            else {
+                                xStar = xs;
+                                if (within_tolerance(ys, target, WVA_BISECT_TOL)) done = true;
+                                else if ((inc && target < ys) || (!inc && target > ys)) { hi = xs; cur = 2 * cur; }
+                                else { lo = xs; cur = 2 * cur + 1; }
+                                if (!done && iters == WVA_BISECT_MAXIT) done = true;
+                            }
+                        }
+                    }
+                }
+            }
+            first = false;
+        }
+        if (toSlow) break;
+        // results of the two bisections
+        const bool failT = __shfl_sync(0xffffffffu, (int)failed, 0), failI = __shfl_sync(0xffffffffu, (int)failed, 16);
+        const int indT = __shfl_sync(0xffffffffu, ind, 0), indI = __shfl_sync(0xffffffffu, ind, 16);
+        const float lTTFT = __shfl_sync(0xffffffffu, xStar, 0), lITL = __shfl_sync(0xffffffffu, xStar, 16);
+        if ((tTTFT > 0.0f && (failT || indT < 0))) break;                  // :205-214
+        if ((tITL > 0.0f && (failI || indI < 0))) break;                   // :218-228
+        float lTPS = lambdaMax;
+        if (tTPS > 0.0f) lTPS = lambdaMax * (1.0f - WVA_STABILITY_SAFETY);
+        const float lambda = go_minf(go_minf(lTTFT, lITL), lTPS);
+        const float requestRate = lambda * 1000.0f;
+        // ---- Analyze(requestRate) (:237-241) and Analyze(totalRate/replicas) (allocation.go:148) ----
+        if (requestRate <= 0.0f || requestRate > wp.rateMax) break;        // :135-143 -> Size fails -> nil
+        const float x1 = requestRate / 1000.0f;
+        float totalRate;
+        if (tTPS == 0.0f) totalRate = arrival / 60.0f;
+        else totalRate = tTPS / (float)Kt;
+        const int minRep = sys.srv_min_replicas[s];
+        // guess: throughput == x1 (blocking probability below float32 resolution)
+        const float rateStarGuess = x1 * 1000.0f;
+        long long repGuess = go_f64_to_int(ceil((double)totalRate / (double)rateStarGuess));
+        if (repGuess < (long long)minRep) repGuess = minRep;
+        const float rate2Guess = totalRate / (float)repGuess;
+        const bool rate2GuessOk = !(rate2Guess <= 0.0f) && !(rate2Guess > wp.rateMax);
+        // reuse an evaluation already made at exactly x1 if some lane has one
+        const unsigned have = __ballot_sync(0xffffffffu, lastX == x1);
+        SolveStats st1, st2;
+        bool valid1 = true, valid2 = true, solved = true;
+        {
+            const bool needX1 = (have == 0u);
+            const bool actA = (lane == 0) && needX1, actB = (lane == 1) && rate2GuessOk;
+            SolveStats stl = st;
+            bool v;
+            solved = warp_solve(wp, actA || actB, lane == 0 ? x1 : rate2Guess / 1000.0f, stl, steps, v);
+            if (__any_sync(0xffffffffu, (actA || actB) && !solved)) { toSlow = true; break; }
+            if (needX1) { st1 = shfl_stats(stl, 0); valid1 = __shfl_sync(0xffffffffu, (int)v, 0); }
+            else { st1 = shfl_stats(st, __ffs(have) - 1); valid1 = true; }
+            st2 = shfl_stats(stl, 1); valid2 = __shfl_sync(0xffffffffu, (int)v, 1);
+        }
+        if (!valid1) break;
+        wva_metrics m1; metrics_from(wp, st1, m1);
+        const float rateStar = m1.throughput;
+        long long numReplicas = go_f64_to_int(ceil((double)totalRate / (double)rateStar));
+        if (numReplicas < (long long)minRep) numReplicas = minRep;
+        const long long totalNumInstances = go_muli(num_instances(sys, m, a), numReplicas);
+        const float cost = sys.acc_cost[a] * (float)totalNumInstances;
+        const float rate2 = totalRate / (float)numReplicas;
+        if (rate2 <= 0.0f || rate2 > wp.rateMax) break;                    // Analyze error -> nil
+        if (!(rate2GuessOk && rate2 == rate2Guess)) {
+            // the guess missed: evaluate the real second rate
+            SolveStats stl = st; bool v;
+            solved = warp_solve(wp, lane == 0, rate2 / 1000.0f, stl, steps, v);
+            if (__any_sync(0xffffffffu, lane == 0 && !solved)) { toSlow = true; break; }
+            st2 = shfl_stats(stl, 0); valid2 = __shfl_sync(0xffffffffu, (int)v, 0);
+        }
+        if (!valid2) break;
+        wva_metrics m2; metrics_from(wp, st2, m2);
+        rec.acc = a; rec.numReplicas = numReplicas; rec.batchSize = N;
+        rec.cost = cost; rec.itl = m2.avg_token_time;
+        rec.ttft = m2.avg_wait_time + m2.avg_prefill_time;
+        rec.rho = m2.rho; rec.maxArrv = rateStar / 1000.0f;
+        rec.value = cost;
+        ok = true;
+    } while (false);
+
+    if (ok) rec.value = transition_penalty(sys.srv_cur_acc[s], sys.srv_cur_replicas[s], sys.srv_cur_cost[s], rec.acc,
+                                           rec.numReplicas, rec.cost);
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+    if (lane == 0) {
+        if (toSlow) { ok = false; slow_list[atomicAdd(slow_count, 1)] = pid; }
+        if (!ok) rec = empty_alloc();
+        store_alloc(out, gi, rec);
+        feasible[gi] = ok ? 1 : 0;
+        if (steps) atomicAdd(step_counter, steps);
+    }
+}
+
 // N per pair (0 = no queueing work) — used to order pairs by chain length and to size scratch.
 __global__ void k_pair_batch(DevSystem sys, int s0, int nPairs, long long* __restrict__ nOut) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -69,16 +69,21 @@ def test_queue_size_matches_oracle(wva, oracle, ctx):
     assert (want[3] == 0).sum() > n // 4
 
 
+@pytest.mark.parametrize("warp_max", [0, 16384])
 @pytest.mark.parametrize("seed,S,A", [(21, 300, 4), (22, 64, 8)])
-def test_pairs_match_oracle(wva, oracle, ctx, seed, S, A):
+def test_pairs_match_oracle(wva, oracle, ctx, seed, S, A, warp_max):
+    """both pair kernels: one thread per pair (warp_max 0) and one warp per pair with speculative bisection"""
     img = wva.synth.make_system(S, A, seed=seed, n_types=max(1, A // 2), max_pair_batch=512)
+    ctx.pairs_set_warp_max(warp_max)
     ctx.upload(img)
     got, gfe = ctx.analyze_pairs()
+    ctx.pairs_set_warp_max(16384)
     want, wfe, steps = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
     assert np.array_equal(gfe, wfe)
     _assert_allocs_equal(got, want)
     assert wfe.sum() > S * A // 3
-    assert ctx.pair_steps() <= steps          # truncation never does more work than the reference
+    if warp_max == 0:
+        assert ctx.pair_steps() <= steps      # truncation never does more work than the reference
 
 
 def test_pairs_golden_config1(wva, oracle, ctx):
@@ -96,6 +101,23 @@ def test_pairs_golden_config1(wva, oracle, ctx):
     img.srv_arrival_rpm[0] = 600.0; img.srv_max_batch[0] = 1
     ctx.upload(img)
     assert ctx.analyze_pairs()[1][0] == 0
+
+
+def test_pairs_iteration_budget(wva, oracle, ctx):
+    """a bisection that never meets the 1e-6 tolerance runs all 100 iterations (the survey's H100 case:
+    122 Solves); the speculative walk must stop at exactly the reference's iteration."""
+    c1 = wva.synth.config1()
+    c1.srv_slo_itl[0] = 10.0; c1.srv_slo_ttft[0] = 1000.0
+    c1.perf_alpha[0], c1.perf_beta[0], c1.perf_gamma[0], c1.perf_delta[0] = 7.470, 0.044, 15.415, 0.000337
+    c1.acc_cost[0] = 100.0; c1.srv_arrival_rpm[0] = 6000.0
+    want, wfe, _ = oracle.analyze_pairs(c1)
+    for warp_max in (0, 16384):
+        ctx.pairs_set_warp_max(warp_max)
+        ctx.upload(c1)
+        got, gfe = ctx.analyze_pairs()
+        assert np.array_equal(gfe, wfe) and got.num_replicas[0] == 3
+        _assert_allocs_equal(got, want)
+    ctx.pairs_set_warp_max(16384)
 
 
 def test_pairs_overflow_rescale_path(wva, oracle, ctx):
