@@ -212,8 +212,7 @@ def main():
 
     def step_device():
         """hot path with the image resident in HBM; decisions stay in HBM."""
-        ctx.analyze_pairs(download=False)
-        ctx.analyze_grid_device(R, B, want_cube=True)
+        ctx.analyze(R, B, want_cube=True)            # Server.Calculate for all pairs || candidate sweep
         ctx.solve(unlimited=True, download=False)
         ctx.allocate_by_type()
         allreduce_totals()
@@ -222,8 +221,9 @@ def main():
         """public API with host buffers: H2D image, D2H decisions."""
         ctx.upload(img)
         ctx.set_shard(first, per_rank)
-        pairs = ctx.analyze_pairs()
-        best, _, _ = ctx.analyze_grid(R, B, want_cube=False)
+        ctx.analyze(R, B, want_cube=False)
+        pairs = ctx.pairs_fetch()
+        best = ctx.grid_fetch()
         chosen = ctx.solve(unlimited=True)
         tot = ctx.allocate_by_type()
         allreduce_totals()

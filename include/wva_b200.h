@@ -218,6 +218,12 @@ int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max,
 int wva_analyze_grid_device(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube);
 int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best);
 
+/* Both halves of Analyze in one call: wva_analyze_pairs and wva_analyze_grid_device are independent
+ * and are run concurrently (the sweep on its own stream).  Results stay in HBM:
+ * wva_pairs_fetch / wva_grid_fetch copy them out, wva_solve consumes the pair records in place. */
+int wva_analyze(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube);
+int wva_pairs_fetch(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible);
+
 /* Device addresses of the S*A candidate records of wva_analyze_pairs (dev->... are DEVICE pointers,
  * server-major, same extents as the host variant).  Multi-GPU limited-capacity mode: each rank
  * fills its shard rows, the host all-gathers the rows over NCCL in place, then calls

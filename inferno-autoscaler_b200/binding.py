@@ -22,7 +22,7 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_analyze", "wva_pairs_fetch",
 ]
 
 
@@ -70,6 +70,8 @@ def lib():
         L.wva_grid_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
         L.wva_pairs_set_warp_max.argtypes = [vp, i32]
+        L.wva_analyze.argtypes = [vp, i32, i32, i32]
+        L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
         L.wva_grid_set_tail_cap.argtypes = [vp, i32]
         L.wva_grid_list_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.wva_stream.argtypes = [vp]
@@ -128,6 +130,17 @@ class Context:
         out = abi.AllocArrays(n)
         feasible = np.zeros(n, dtype=np.uint8)
         self._ck(lib().wva_analyze_pairs(self._h, C.byref(out.c), abi.ptr(feasible, C.c_uint8)))
+        return out, feasible
+
+    def analyze(self, r_max, b_max, want_cube=False):
+        """Server.Calculate for every pair and the candidate sweep, overlapped; results stay on the device."""
+        self._ck(lib().wva_analyze(self._h, int(r_max), int(b_max), 1 if want_cube else 0))
+
+    def pairs_fetch(self):
+        n = self.image.S * self.image.A
+        out = abi.AllocArrays(n)
+        feasible = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().wva_pairs_fetch(self._h, C.byref(out.c), abi.ptr(feasible, C.c_uint8)))
         return out, feasible
 
     def pairs_set_warp_max(self, n):

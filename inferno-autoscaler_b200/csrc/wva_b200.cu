@@ -4,9 +4,12 @@
 // implementation of any arithmetic in this file (and no fallback when CUDA is unavailable).
 #include "wva_kernels.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace wva;
@@ -48,9 +51,12 @@ struct PinnedBuf {
 struct wva_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t gstream = nullptr;      // the candidate sweep has its own stream so it can overlap the pair sizing
+    cudaEvent_t evg0 = nullptr, evg1 = nullptr, evJoin = nullptr, evFork = nullptr;
+    std::mutex errMutex;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     std::string err;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};
     int64_t phase_usec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     // system image
@@ -74,7 +80,7 @@ struct wva_ctx {
 
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
-    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot;
+    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch;
     int grid_tail_cap = 192; int last_heavy = 0, last_slow = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     int grid_r = 0, grid_b = 0; bool grid_valid = false;
@@ -87,7 +93,7 @@ struct wva_ctx {
 namespace {
 
 int fail(wva_ctx* c, int code, const std::string& msg) {
-    if (c) c->err = msg; else g_create_error = msg;
+    if (c) { std::lock_guard<std::mutex> g(c->errMutex); c->err = msg; } else g_create_error = msg;
     return code;
 }
 #define CK(expr)                                                                                   \
@@ -106,14 +112,15 @@ int fail(wva_ctx* c, int code, const std::string& msg) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct PhaseTimer {
-    wva_ctx* c; int phase;
-    PhaseTimer(wva_ctx* c_, int p) : c(c_), phase(p) { cudaEventRecord(c->ev0, c->stream); }
+    wva_ctx* c; int phase; cudaStream_t st; cudaEvent_t e0, e1;
+    PhaseTimer(wva_ctx* c_, int p) : c(c_), phase(p), st(c_->stream), e0(c_->ev0), e1(c_->ev1) { cudaEventRecord(e0, st); }
+    PhaseTimer(wva_ctx* c_, int p, cudaStream_t s, cudaEvent_t a, cudaEvent_t b) : c(c_), phase(p), st(s), e0(a), e1(b) { cudaEventRecord(e0, st); }
     // call after the stream has been synchronised (or will be by the event sync below)
     void stop() {
-        cudaEventRecord(c->ev1, c->stream);
-        cudaEventSynchronize(c->ev1);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
         float ms = 0.0f;
-        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        cudaEventElapsedTime(&ms, e0, e1);
         c->phase_usec[phase] = (int64_t)(ms * 1000.0f + 0.5f);
     }
 };
@@ -179,7 +186,11 @@ int wva_ctx_create(int device, wva_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->evh0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evh1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->evh0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evh1)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->evg0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evg1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess) {
         std::string msg = std::string("stream/event create: ") + cudaGetErrorString(e);
         delete ctx;
         return fail(nullptr, WVA_ECUDA, msg);
@@ -196,7 +207,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
                       &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
-                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->ioA, &ctx->ioB,
+                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->ioA, &ctx->ioB,
                       &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG};
     for (DevBuf* b : bufs) b->release();
     ctx->staging.release();
@@ -206,12 +217,17 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaEventDestroy(ctx->evk1);
     cudaEventDestroy(ctx->evh0);
     cudaEventDestroy(ctx->evh1);
+    cudaEventDestroy(ctx->evg0);
+    cudaEventDestroy(ctx->evg1);
+    cudaEventDestroy(ctx->evJoin);
+    cudaEventDestroy(ctx->evFork);
+    cudaStreamDestroy(ctx->gstream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 void* wva_stream(const wva_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int64_t wva_launch_count(const wva_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t wva_launch_count(const wva_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase) { return (ctx && phase >= 0 && phase < 8) ? ctx->phase_usec[phase] : 0; }
 int64_t wva_solution_time_usec(const wva_ctx* ctx) { return ctx ? ctx->phase_usec[WVA_PHASE_SOLVE] : 0; }
 
@@ -421,7 +437,7 @@ int wva_pair_steps(wva_ctx* ctx, uint64_t* steps) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool want_status) {
+static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool want_status, bool fork_join = true) {
     if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
     if (r_max < 1 || r_max > WVA_GRID_MAX_R || b_max < 1 || b_max > WVA_GRID_MAX_B || ctx->A > WVA_GRID_MAX_A)
         return fail(ctx, WVA_EINVAL, "grid extents out of range (A<=256, r_max<=1024, b_max<=8192)");
@@ -497,13 +513,18 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     gp.block_slot = ctx->blockSlot.as<GridSlot>();
     const long long stride = 11LL * b_max + 1;
 
-    PhaseTimer timer(ctx, WVA_PHASE_GRID);
+    // order the sweep after whatever the main stream has queued (the system upload), run it on its own stream
+    if (fork_join) {
+        CK(cudaEventRecord(ctx->evFork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->gstream, ctx->evFork, 0));
+    }
+    PhaseTimer timer(ctx, WVA_PHASE_GRID, ctx->gstream, ctx->evg0, ctx->evg1);
     ctx->phase_usec[WVA_PHASE_GRID_KERNEL] = 0; ctx->phase_usec[WVA_PHASE_GRID_HEAVY] = 0;
     ctx->last_heavy = 0; ctx->last_slow = 0;
-    CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->gstream));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->gstream));
     if (ns > 0) {
-        k_grid_best_init<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ns, ctx->bestDev.as<wva_grid_best>());
+        k_grid_best_init<<<(ns + 255) / 256, 256, 0, ctx->gstream>>>(ns, ctx->bestDev.as<wva_grid_best>());
         LAUNCH_CHECK();
     }
     for (int sBeg = 0; sBeg < ns; sBeg += srvPerSlice) {
@@ -515,13 +536,13 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         int slow = 0, heavy = 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
-            CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->stream));
-            CK(cudaEventRecord(ctx->evk0, ctx->stream));
-            k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->stream>>>(ctx->dsys, gp);
+            CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
+            CK(cudaEventRecord(ctx->evk0, ctx->gstream));
+            k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
-            CK(cudaEventRecord(ctx->evk1, ctx->stream));
-            CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaEventRecord(ctx->evk1, ctx->gstream));
+            CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->gstream));
+            CK(cudaStreamSynchronize(ctx->gstream));
             slow = counts[0]; heavy = counts[1] < heavy_cap ? counts[1] : heavy_cap;
             {
                 float kms = 0.0f;
@@ -533,20 +554,20 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             if (heavy > 0) {
                 // long chains: order by estimated length (longest first), one thread per chain
                 int* hist = ctx->heavyHist.as<int>();
-                CK(cudaEventRecord(ctx->evh0, ctx->stream));
-                CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->stream));
-                k_heavy_hist<<<(heavy + 255) / 256, 256, 0, ctx->stream>>>(gp.heavy_cost, heavy, hist);
+                CK(cudaEventRecord(ctx->evh0, ctx->gstream));
+                CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->gstream));
+                k_heavy_hist<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist);
                 LAUNCH_CHECK();
-                k_heavy_prefix<<<1, 256, 0, ctx->stream>>>(hist);
+                k_heavy_prefix<<<1, 256, 0, ctx->gstream>>>(hist);
                 LAUNCH_CHECK();
-                k_heavy_scatter<<<(heavy + 255) / 256, 256, 0, ctx->stream>>>(gp.heavy_cost, heavy, hist, ctx->heavyOrder.as<int>());
+                k_heavy_scatter<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist, ctx->heavyOrder.as<int>());
                 LAUNCH_CHECK();
-                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, gp, gp.heavy_list, ctx->heavyOrder.as<int>(), heavy,
+                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, ctx->heavyOrder.as<int>(), heavy,
                                                                         nullptr, 0, 0);
                 LAUNCH_CHECK();
-                CK(cudaEventRecord(ctx->evh1, ctx->stream));
-                CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
+                CK(cudaEventRecord(ctx->evh1, ctx->gstream));
+                CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->gstream));
+                CK(cudaStreamSynchronize(ctx->gstream));
                 slow = counts[0];
                 float hms = 0.0f;
                 CK(cudaEventElapsedTime(&hms, ctx->evh0, ctx->evh1));
@@ -568,28 +589,33 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             size_t maxItems = (freeB / 2) / per;
             if (maxItems == 0) return fail(ctx, WVA_ECUDA, "not enough device memory for the materialised chain path");
             if (maxItems > (size_t)slow) maxItems = (size_t)slow;
-            CK(ctx->scratch.ensure(maxItems * per));
+            CK(ctx->gscratch.ensure(maxItems * per));
             for (size_t done = 0; done < (size_t)slow; done += maxItems) {
                 int n = (int)(((size_t)slow - done) < maxItems ? ((size_t)slow - done) : maxItems);
-                k_grid_list<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, gp, ctx->gridSlow.as<unsigned long long>() + done, nullptr,
-                                                                   n, ctx->scratch.as<double>(), stride, heavy + (int)done);
+                k_grid_list<<<(n + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, ctx->gridSlow.as<unsigned long long>() + done, nullptr,
+                                                                   n, ctx->gscratch.as<double>(), stride, heavy + (int)done);
                 LAUNCH_CHECK();
             }
             listSlots += slow;
         }
         // winners of the slice: the slot that carries a server's minimum key writes its record
         if (nBlocks > 0) {
-            k_grid_claim<<<(unsigned)((nBlocks + 255) / 256), 256, 0, ctx->stream>>>(gp, gp.block_slot, (int)nBlocks, ctx->bestDev.as<wva_grid_best>());
+            k_grid_claim<<<(unsigned)((nBlocks + 255) / 256), 256, 0, ctx->gstream>>>(gp, gp.block_slot, (int)nBlocks, ctx->bestDev.as<wva_grid_best>());
             LAUNCH_CHECK();
         }
         if (listSlots > 0) {
-            k_grid_claim<<<(listSlots + 255) / 256, 256, 0, ctx->stream>>>(gp, gp.list_slot, listSlots, ctx->bestDev.as<wva_grid_best>());
+            k_grid_claim<<<(listSlots + 255) / 256, 256, 0, ctx->gstream>>>(gp, gp.list_slot, listSlots, ctx->bestDev.as<wva_grid_best>());
             LAUNCH_CHECK();
         }
     }
-    CK(cudaMemcpyAsync(ctx->grid_counters, ctx->counters.p, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->grid_counters, ctx->counters.p, 3 * 8, cudaMemcpyDeviceToHost, ctx->gstream));
+    CK(cudaStreamSynchronize(ctx->gstream));
     timer.stop();
+    // later work on the main stream sees the sweep's results
+    if (fork_join) {
+        CK(cudaEventRecord(ctx->evJoin, ctx->gstream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    }
     ctx->grid_r = r_max; ctx->grid_b = b_max; ctx->grid_valid = true;
     return WVA_OK;
 }
@@ -605,6 +631,40 @@ int wva_grid_fetch(wva_ctx* ctx, wva_grid_best* best) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->ns > 0) {
         CK(cudaMemcpyAsync(best, ctx->bestDev.p, (size_t)ctx->ns * sizeof(wva_grid_best), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return WVA_OK;
+}
+
+// Analyze, both halves at once: Server.Calculate for every pair (main stream) and the candidate
+// sweep (its own stream, driven by a helper host thread) are independent and overlap on the device.
+// Results stay in HBM; fetch them with wva_pairs_fetch / wva_grid_fetch.
+int wva_analyze(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    CK(cudaSetDevice(ctx->device));
+    // fork: the sweep starts after what the main stream holds now (the upload), not after the pair kernels
+    CK(cudaEventRecord(ctx->evFork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->gstream, ctx->evFork, 0));
+    int rcGrid = WVA_OK;
+    const int dev = ctx->device;
+    std::thread sweep([&] { cudaSetDevice(dev); rcGrid = grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0, false); });
+    int rcPairs = wva_analyze_pairs(ctx, nullptr, nullptr);
+    sweep.join();
+    // join: later work on the main stream sees the sweep's results
+    CK(cudaEventRecord(ctx->evJoin, ctx->gstream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    return rcPairs != WVA_OK ? rcPairs : rcGrid;
+}
+
+int wva_pairs_fetch(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "analyze_pairs has not run (or a limited solve consumed its records)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nPairs = (size_t)ctx->ns * ctx->A, first = (size_t)ctx->s0 * ctx->A;
+    if (nPairs > 0) {
+        if (out) CK(download_allocs(ctx, ctx->pairs, first, nPairs, out, first));
+        if (feasible) CK(cudaMemcpyAsync(feasible + first, ctx->feasible + first, nPairs, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return WVA_OK;

@@ -359,6 +359,8 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         if (searching && lambdaMin > lambdaMax) { failed = true; done = true; }     // utils.go:29-31
         SolveStats st; st.rho = st.avgNumInServers = st.avgNumInSystem = st.throughput = st.avgRespTime = st.avgServTime = st.avgWaitTime = 0.0f;
         float lastX = -1.0f;                           // this lane's most recent evaluation point
+        float ylo = 0.0f, yhi = 0.0f;                  // eval(lo), eval(hi): always known after the first round,
+                                                       // so a midpoint that rounds onto an endpoint costs nothing
         bool first = true;
         while (__any_sync(0xffffffffu, !done)) {
             // --- choose this lane's evaluation point ---
@@ -371,6 +373,14 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                 } else if (hl >= 1) { node = hl; act = true; x = bisect_node_x(lo, hi, node); }
                 // never evaluate beyond the reference's iteration budget
                 if (node > 0 && (31 - __clz(node)) >= WVA_BISECT_MAXIT - iters) act = false;
+                // a midpoint equal to an endpoint of its own interval has a known value.  Endpoints of
+                // deeper nodes are midpoints of shallower ones, so it is enough to test against the
+                // node's own [lo', hi']: recompute them along the path.
+                if (node > 0 && act) {
+                    float l2 = lo, h2 = hi, xm = 0.5f * (lo + hi);
+                    for (int l = (31 - __clz(node)) - 1; l >= 0; --l) { if ((node >> l) & 1) l2 = xm; else h2 = xm; xm = 0.5f * (l2 + h2); }
+                    if (xm == l2 || xm == h2) act = false;      // resolved from the memo while walking
+                }
             }
             bool valid;
             bool solved = warp_solve(wp, act, x, st, steps, valid);
@@ -388,6 +398,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                     else if (within_tolerance(yb1, target, WVA_BISECT_TOL)) { xStar = hi; ind = 0; done = true; }
                     else {
                         inc = yb0 < yb1;
+                        ylo = yb0; yhi = yb1;
                         if ((inc && target < yb0) || (!inc && target > yb0)) { xStar = lo; ind = -1; done = true; }
                         else if ((inc && target > yb1) || (!inc && target < yb1)) { xStar = hi; ind = +1; done = true; }
                     }
@@ -398,19 +409,20 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                 int cur = 1;
                 for (int l = 0; l < levels; ++l) {
                     const int src = base + (first ? cur + 1 : cur);
-                    const float ys = __shfl_sync(0xffffffffu, y, src);
-                    const bool vs = __shfl_sync(0xffffffffu, (int)valid, src);
+                    float ys = __shfl_sync(0xffffffffu, y, src);
+                    bool vs = __shfl_sync(0xffffffffu, (int)valid, src);
                     if (!done) {
                         if (iters == WVA_BISECT_MAXIT) { done = true; }
                         else {
                             const float xs = 0.5f * (lo + hi);
+                            if (xs == lo) { ys = ylo; vs = true; } else if (xs == hi) { ys = yhi; vs = true; }
                             ++iters;
                             if (!vs) { failed = true; done = true; }
                             else {
                                 xStar = xs;
                                 if (within_tolerance(ys, target, WVA_BISECT_TOL)) done = true;
-                                else if ((inc && target < ys) || (!inc && target > ys)) { hi = xs; cur = 2 * cur; }
-                                else { lo = xs; cur = 2 * cur + 1; }
+                                else if ((inc && target < ys) || (!inc && target > ys)) { hi = xs; yhi = ys; cur = 2 * cur; }
+                                else { lo = xs; ylo = ys; cur = 2 * cur + 1; }
                                 if (!done && iters == WVA_BISECT_MAXIT) done = true;
                             }
                         }

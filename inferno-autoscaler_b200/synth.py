@@ -21,7 +21,7 @@ SERVICE_CLASSES = [(24.0, 500.0, 1), (80.0, 1000.0, 5), (200.0, 2000.0, 10)]
 
 def make_system(n_servers, n_accels, seed, n_types=None, one_model_per_server=True, n_models=None,
                 edge_fraction=0.02, tps_fraction=0.10, zero_load_fraction=0.02, keep_fraction=0.10,
-                max_pair_batch=4096):
+                max_pair_batch=512):
     """Random system image.  `max_pair_batch` bounds N = maxBatch*atTokens/outTokens of the
     reference sizing path (pkg/core/allocation.go:85) through a server-level batch override, so
     one pathological pair cannot dominate a whole run (N has no upper bound in the reference)."""

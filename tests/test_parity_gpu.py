@@ -244,6 +244,23 @@ def test_solve_greedy_ties(wva, oracle, ctx):
         _assert_allocs_equal(chosen, w_chosen)
 
 
+def test_overlapped_analyze_equals_separate_calls(wva, oracle, ctx):
+    """wva_analyze runs the pair sizing and the candidate sweep concurrently on two streams"""
+    img = wva.synth.make_system(40, 3, seed=71)
+    ctx.upload(img)
+    ctx.analyze(8, 40, want_cube=False)
+    pairs, fe = ctx.pairs_fetch()
+    best = ctx.grid_fetch()
+    want, wfe, _ = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
+    w_best, _, _, _ = oracle.analyze_grid(img, 8, 40, want_cube=False, threads=oracle.hardware_threads())
+    assert np.array_equal(fe, wfe)
+    _assert_allocs_equal(pairs, want)
+    assert best.tobytes() == w_best.tobytes()
+    acc, chosen = ctx.solve(unlimited=True)
+    w_acc, w_chosen = oracle.solve(img, want, wfe, unlimited=True)
+    assert np.array_equal(acc, w_acc)
+
+
 def test_state_errors(wva, ctx):
     from inferno_autoscaler_b200 import binding
     img = wva.synth.make_system(4, 2, seed=1)
