@@ -1,0 +1,63 @@
+"""GPU: the C++ host mirror of the reference's Go API (inferno-autoscaler_b200/host) drives the
+reconcile call sequence of internal/controller (variantautoscaling_controller.go:143-166) over the
+C-ABI; results are checked against the oracle and the reference's integration-test expectations."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F = np.float32
+
+
+def _run():
+    import __graft_entry__ as g
+    g.build_cuda(); g.build_host()
+    exe = os.path.join(ROOT, "inferno-autoscaler_b200", "host", "host_test")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return {d["scenario"]: d for d in map(json.loads, out.stdout.strip().splitlines())}
+
+
+def _spec(arrival, out_tok, itl, ttft, two_acc=False):
+    accs = [{"name": "A100", "type": "A100", "multiplicity": 1, "cost": 40.0}]
+    models = [{"name": "m", "acc": "A100", "accCount": 1, "maxBatchSize": 4, "atTokens": 0,
+               "decodeParms": {"alpha": 20.28, "beta": 0.72}, "prefillParms": {"gamma": 0, "delta": 0}}]
+    if two_acc:
+        accs.append({"name": "H100", "type": "H100", "multiplicity": 1, "cost": 100.0})
+        models.append({"name": "m", "acc": "H100", "accCount": 1, "maxBatchSize": 4, "atTokens": 0,
+                       "decodeParms": {"alpha": 7.47, "beta": 0.044}, "prefillParms": {"gamma": 0, "delta": 0}})
+    return {
+        "acceleratorData": {"accelerators": accs}, "modelData": {"models": models},
+        "serviceClassData": {"serviceClasses": [{"name": "Premium", "priority": 1, "modelTargets": [
+            {"model": "m", "slo-itl": itl, "slo-ttft": ttft}]}]},
+        "serverData": {"servers": [{"name": "va:default", "class": "Premium", "model": "m", "keepAccelerator": not two_acc,
+                                    "minNumReplicas": 1, "maxBatchSize": 4,
+                                    "currentAlloc": {"accelerator": "A100", "numReplicas": 1, "cost": 40.0,
+                                                     "load": {"arrivalRate": arrival, "avgInTokens": 20, "avgOutTokens": out_tok}}}]},
+        "capacityData": {"count": [{"type": "A100", "count": 10}, {"type": "H100", "count": 8}] if two_acc else []},
+    }
+
+
+def test_reconcile_sequence_through_cpp_host(wva, oracle):
+    r = _run()
+    # internal/optimizer/optimizer_test.go:333: no load => replicas == minNumReplicas
+    assert r["no_load"]["error"] is None and r["no_load"]["optimized"]["va"]["replicas"] == 1
+    # :455: 20 req/s => replicas > 1 (43 with the survey's derived vector), keyed by bare va.Name
+    so = r["scale_out"]["optimized"]["va"]
+    assert so["accelerator"] == "A100" and so["replicas"] == 43
+    assert F(so["itl"]) == F(22.345161) and F(so["ttft"]) == F(496.41406) and F(so["cost"]) == F(1720.0)
+    assert r["scale_out"]["by_type"]["A100"]["count"] == 43
+    # infeasible SLO => CreateAllocation nil => empty solution => the error of optimizer.go:38-40
+    assert r["infeasible_slo"]["error"]["code"] == wva.abi.ENOSOLUTION and r["infeasible_slo"]["analyze_allocations"] == 0
+    # limited capacity, greedy + PriorityExhaustive against the oracle
+    img = wva.SystemImage.from_spec(_spec(1200.0, 200, 80.0, 500.0, two_acc=True))
+    pairs, feas, _ = oracle.analyze_pairs(img)
+    acc, chosen = oracle.solve(img, pairs, feas, unlimited=False, policy=wva.abi.POLICY_PRIORITY_EXHAUSTIVE)
+    lg = r["limited_greedy"]["optimized"]["va"]
+    assert r["limited_greedy"]["analyze_allocations"] == int(feas.sum())
+    assert lg["accelerator"] == img.acc_names[chosen.acc[0]] and lg["replicas"] == int(chosen.num_replicas[0])
+    assert F(lg["cost"]) == chosen.cost[0] and F(lg["itl"]) == chosen.itl[0]
