@@ -232,10 +232,21 @@ int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
 int wva_pairs_commit(wva_ctx* ctx);
 /* Tuning: shards with at most max_pairs (server, accelerator) pairs use the warp-per-pair kernel
  * (speculative bisection, lowest latency); larger shards use one thread per pair (highest
- * throughput).  Results do not depend on it.  Default 16384; 0 = always thread-per-pair. */
+ * throughput).  Results do not depend on it.  Default 2^22 (measured: the warp kernel is ~30x faster than thread-per-pair even at 8 000 pairs
+ * because its lanes stay converged); 0 = always thread-per-pair. */
 int wva_pairs_set_warp_max(wva_ctx* ctx, int32_t max_pairs);
+/* Tuning (warp-per-pair kernel): keep the chain values of pass 1 in HBM and read them back in pass 2
+ * instead of re-running the recurrence.  Same results; off by default (measured slower on B200: the
+ * loads expose L2 latency that the recomputation does not have). */
+int wva_pairs_set_pstore(wva_ctx* ctx, int32_t on);
 /* Chain-state updates executed by the last wva_analyze_pairs (instrumentation). */
 int wva_pair_steps(wva_ctx* ctx, uint64_t* steps);
+/* warp-per-pair kernel counters: {chain steps, sum of bisection rounds over pairs, max rounds of a pair,
+ * trailing-Analyze evaluations that the cache / guess did not cover (+100 per missed guess)}. */
+int wva_pair_counters(wva_ctx* ctx, uint64_t out[4]);
+/* With wva_pairs_set_pstore(ctx, 4) set before wva_analyze_pairs: per pair of the shard, SM cycles spent
+ * and (rounds << 32) | rounds-with-evaluations of the warp-per-pair kernel (profiling aid). */
+int wva_pair_debug(wva_ctx* ctx, uint64_t* out, int32_t n_pairs);
 
 /* ---- Optimize ------------------------------------------------------------ */
 

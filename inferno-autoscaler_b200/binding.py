@@ -19,10 +19,10 @@ _lib = None
 # every symbol include/wva_b200.h declares (tests/test_abi_symbols.py checks the header against this)
 EXPORTS = [
     "wva_abi_version", "wva_ctx_create", "wva_ctx_destroy", "wva_last_error", "wva_system_upload", "wva_set_shard",
-    "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_analyze_grid",
+    "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_pair_counters", "wva_pair_debug", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_analyze", "wva_pairs_fetch",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_analyze", "wva_pairs_fetch",
 ]
 
 
@@ -53,6 +53,8 @@ def lib():
         L.wva_pairs_device.argtypes = [vp, C.POINTER(abi.AllocSoa), C.POINTER(vp)]
         L.wva_pairs_commit.argtypes = [vp]
         L.wva_pair_steps.argtypes = [vp, C.POINTER(u64)]
+        L.wva_pair_counters.argtypes = [vp, C.POINTER(u64)]
+        L.wva_pair_debug.argtypes = [vp, C.POINTER(u64), i32]
         L.wva_analyze_grid.argtypes = [vp, i32, i32, vp, vp, vp]
         L.wva_analyze_grid_device.argtypes = [vp, i32, i32, i32]
         L.wva_grid_fetch.argtypes = [vp, vp]
@@ -70,6 +72,7 @@ def lib():
         L.wva_grid_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
         L.wva_pairs_set_warp_max.argtypes = [vp, i32]
+        L.wva_pairs_set_pstore.argtypes = [vp, i32]
         L.wva_analyze.argtypes = [vp, i32, i32, i32]
         L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
         L.wva_grid_set_tail_cap.argtypes = [vp, i32]
@@ -142,6 +145,20 @@ class Context:
         feasible = np.zeros(n, dtype=np.uint8)
         self._ck(lib().wva_pairs_fetch(self._h, C.byref(out.c), abi.ptr(feasible, C.c_uint8)))
         return out, feasible
+
+    def pair_counters(self):
+        v = (C.c_uint64 * 4)()
+        self._ck(lib().wva_pair_counters(self._h, v))
+        return dict(steps=v[0], rounds_sum=v[1], rounds_max=v[2], trailing=v[3])
+
+    def pair_debug(self):
+        n = self.count * self.image.A
+        out = np.zeros(2 * n, dtype=np.uint64)
+        self._ck(lib().wva_pair_debug(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+        return out.reshape(n, 2)
+
+    def pairs_set_pstore(self, on):
+        self._ck(lib().wva_pairs_set_pstore(self._h, int(on)))
 
     def pairs_set_warp_max(self, n):
         self._ck(lib().wva_pairs_set_warp_max(self._h, int(n)))

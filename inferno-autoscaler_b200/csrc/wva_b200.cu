@@ -70,8 +70,12 @@ struct wva_ctx {
     // pair results (full S*A extent; a rank fills its shard rows)
     DevBuf pairBuf; DevAllocs pairs{}; unsigned char* feasible = nullptr;
     bool pairs_valid = false; bool pairs_complete = false;
-    DevBuf pairN, pairOrder, pairHist, slowList, slowCount, stepCounter, scratch, scratchOff, pairTabs, pairTabOff;
-    int pairs_warp_max = 16384;
+    DevBuf pairN, pairOrder, pairHist, slowList, slowCount, stepCounter, scratch, scratchOff, pairTabs, pairTabOff, pairPbuf;
+    int pairs_warp_max = 1 << 22;
+    int pairs_pstore = 0;
+    int pairs_smem = 1;
+    int pairs_debug = 0;
+    DevBuf pairDbg;
 
     // solution
     DevBuf chosenBuf; DevAllocs chosen{}; int* chosen_acc = nullptr; bool solved = false;
@@ -204,7 +208,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
-                      &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->chosenBuf, &ctx->totals,
+                      &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->pairPbuf, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
                       &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->ioA, &ctx->ioB,
@@ -307,11 +311,11 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
     CK(carve_allocs(ctx->pairBuf, nAll ? nAll : 1, ctx->pairs, &ctx->feasible, nullptr));
     CK(ctx->slowList.ensure((size_t)(nPairs ? nPairs : 1) * 4));
     CK(ctx->slowCount.ensure(4));
-    CK(ctx->stepCounter.ensure(8));
+    CK(ctx->stepCounter.ensure(32));
     CK(ctx->pairN.ensure((size_t)(nPairs ? nPairs : 1) * 8));
     PhaseTimer timer(ctx, WVA_PHASE_PAIRS);
     CK(cudaMemsetAsync(ctx->slowCount.p, 0, 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->stepCounter.p, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stepCounter.p, 0, 32, ctx->stream));
     int slow = 0;
     if (nPairs > 0) {
         k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
@@ -321,10 +325,11 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
             std::vector<long long> nHost((size_t)nPairs), offs((size_t)nPairs);
             CK(cudaMemcpyAsync(nHost.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            long long total = 0;
+            long long total = 0, maxN = 0;
             const long long budget = (2LL << 30) / 16;          // at most 2 GB of tables
             for (int i = 0; i < nPairs; ++i) {
                 long long N = nHost[(size_t)i];
+                if (N > maxN && N <= (1LL << 26)) maxN = N;
                 if (N <= 0) { offs[(size_t)i] = 0; continue; }   // pair does no queueing work: offset unused
                 if (N > (1LL << 26) || total + N > budget) { offs[(size_t)i] = -1; continue; }
                 offs[(size_t)i] = total; total += N;
@@ -333,9 +338,24 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
             CK(ctx->pairTabOff.ensure((size_t)nPairs * 8));
             CK(cudaMemcpyAsync(ctx->pairTabOff.p, offs.data(), (size_t)nPairs * 8, cudaMemcpyHostToDevice, ctx->stream));
             const int warpsPerBlock = WVA_PAIRS_WARP_THREADS / 32;
-            k_pairs_warp<<<(nPairs + warpsPerBlock - 1) / warpsPerBlock, WVA_PAIRS_WARP_THREADS, 0, ctx->stream>>>(
+            // shared-memory tables: up to 3072 entries (48 KB) per warp, 4 warps per block
+            int smemEntries = ctx->pairs_smem ? (int)(maxN < 3072 ? maxN : 3072) : 0;
+            const size_t smemBytes = (size_t)smemEntries * 16 * warpsPerBlock;
+            if (smemBytes > 48 * 1024)
+                CK(cudaFuncSetAttribute(k_pairs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+            // chain-value buffers (pass 2 reads p[n] back instead of re-running the recurrence): one
+            // [K+1][32] block per pair while that stays under 4 GB
+            const long long strideK = 11 * maxN + 1;
+            double* pbuf = nullptr;
+            if (ctx->pairs_pstore && maxN > 0 && (double)nPairs * (double)strideK * 256.0 <= 4.0 * (1u << 30)) {
+                CK(ctx->pairPbuf.ensure((size_t)nPairs * (size_t)strideK * 256));
+                pbuf = ctx->pairPbuf.as<double>();
+            }
+            if (ctx->pairs_debug) CK(ctx->pairDbg.ensure((size_t)nPairs * 16));
+            k_pairs_warp<<<(nPairs + warpsPerBlock - 1) / warpsPerBlock, WVA_PAIRS_WARP_THREADS, smemBytes, ctx->stream>>>(
                 ctx->dsys, ctx->s0, nPairs, ctx->pairTabOff.as<long long>(), ctx->pairTabs.as<double2>(), ctx->pairs, ctx->feasible,
-                ctx->slowList.as<int>(), ctx->slowCount.as<int>(), ctx->stepCounter.as<unsigned long long>());
+                ctx->slowList.as<int>(), ctx->slowCount.as<int>(), ctx->stepCounter.as<unsigned long long>(), smemEntries, pbuf, strideK,
+                ctx->pairs_debug ? ctx->pairDbg.as<unsigned long long>() : nullptr);
             LAUNCH_CHECK();
         } else {
         const int* order = nullptr;
@@ -423,6 +443,13 @@ int wva_pairs_commit(wva_ctx* ctx) {
     ctx->pairs_complete = true;
     return WVA_OK;
 }
+int wva_pairs_set_pstore(wva_ctx* ctx, int32_t on) {
+    if (!ctx) return WVA_EINVAL;
+    ctx->pairs_pstore = (on & 1) ? 1 : 0;
+    ctx->pairs_smem = (on & 2) ? 0 : 1;        // bit 1: keep the tables in HBM instead of shared memory (tuning/debug)
+    ctx->pairs_debug = (on & 4) ? 1 : 0;       // bit 2: record per-pair cycles / rounds (wva_pair_debug)
+    return WVA_OK;
+}
 int wva_pairs_set_warp_max(wva_ctx* ctx, int32_t max_pairs) {
     if (!ctx || max_pairs < 0) return WVA_EINVAL;
     ctx->pairs_warp_max = max_pairs;
@@ -433,6 +460,21 @@ int wva_pair_steps(wva_ctx* ctx, uint64_t* steps) {
     if (!ctx->stepCounter.p) { *steps = 0; return WVA_OK; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpy(steps, ctx->stepCounter.p, 8, cudaMemcpyDeviceToHost));
+    return WVA_OK;
+}
+int wva_pair_debug(wva_ctx* ctx, uint64_t* out /* 2 per pair of the shard: cycles, (rounds<<32)|rounds with evaluations */, int32_t n_pairs) {
+    if (!ctx || !out) return WVA_EINVAL;
+    if (!ctx->pairDbg.p || (size_t)n_pairs * 16 > ctx->pairDbg.cap) return fail(ctx, WVA_ESTATE, "no debug record");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->pairDbg.p, (size_t)n_pairs * 16, cudaMemcpyDeviceToHost));
+    return WVA_OK;
+}
+// instrumentation of the warp-per-pair kernel: {chain steps, sum of bisection rounds, max rounds, trailing-Analyze misses}
+int wva_pair_counters(wva_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return WVA_EINVAL;
+    if (!ctx->stepCounter.p) { out[0] = out[1] = out[2] = out[3] = 0; return WVA_OK; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->stepCounter.p, 32, cudaMemcpyDeviceToHost));
     return WVA_OK;
 }
 
@@ -452,10 +494,11 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     CK(ctx->gridSlowCount.ensure(8));                 // [0] literal-path count, [1] deferred count
     CK(ctx->heavyHist.ensure(2 * 256 * 4));
     if (want_cube) {
-        size_t freeB = 0, totB = 0;
-        CK(cudaMemGetInfo(&freeB, &totB));
-        if (nCand * sizeof(wva_metrics) > ctx->cube.cap && nCand * sizeof(wva_metrics) > freeB - (freeB >> 3))
-            return fail(ctx, WVA_ECUDA, "metric cube does not fit in device memory");
+        if (nCand * sizeof(wva_metrics) > ctx->cube.cap) {
+            size_t freeB = 0, totB = 0;
+            CK(cudaMemGetInfo(&freeB, &totB));
+            if (nCand * sizeof(wva_metrics) > freeB - (freeB >> 3)) return fail(ctx, WVA_ECUDA, "metric cube does not fit in device memory");
+        }
         CK(ctx->cube.ensure(nCand * sizeof(wva_metrics)));
     }
     if (want_status) CK(ctx->status.ensure(nCand ? nCand : 1));

@@ -247,6 +247,7 @@ __device__ __forceinline__ float bisect_node_x(float lo, float hi, int node) {
 
 struct WarpPair {
     ServFormula sv; ProvTableF pv;
+    double* pstore;                 // this lane's column of the warp's chain-value buffer, or nullptr
     int N, K; long long inTok, outTok; bool tame;
     float rateMin, rateMax;
 };
@@ -255,7 +256,7 @@ struct WarpPair {
 // lane's chain needs the materialised path
 __device__ __forceinline__ bool warp_solve(const WarpPair& wp, bool active, float x, SolveStats& st, unsigned long long& steps,
                                            bool& valid) {
-    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active);
+    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active, wp.pstore);
     valid = true;
     if (!active) return true;
     if (x < 0.0f) { valid = false; return true; }                       // queuemodel.go:31 (stale rho is in [0,1] < K)
@@ -296,7 +297,11 @@ __device__ __forceinline__ SolveStats shfl_stats(const SolveStats& s, int src) {
 #define WVA_PAIRS_WARP_THREADS 128
 __global__ void __launch_bounds__(WVA_PAIRS_WARP_THREADS)
 k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ tabOff, double2* tabs, DevAllocs out,
-             unsigned char* feasible, int* slow_list, int* slow_count, unsigned long long* step_counter) {
+             unsigned char* feasible, int* slow_list, int* slow_count, unsigned long long* step_counter,
+             int smemEntriesPerWarp, double* pbuf, long long pbufStrideK, unsigned long long* dbg) {
+    extern __shared__ __align__(16) unsigned char pairs_smem[];
+    const long long tStart = clock64();
+    int activeRounds = 0, totalRounds = 0;
     const int pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp-uniform
     const int lane = threadIdx.x & 31;
     if (pid >= nPairs) return;
@@ -328,7 +333,11 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         wp.sv.init(sp, inTok, Kt);
         wp.N = (int)N; wp.K = (int)(maxQueue + N); wp.inTok = inTok; wp.outTok = Kt;
         wp.tame = tame_parms(sp, inTok, Kt);
-        double2* tab = tabs + tabOff[pid];
+        // the table lives in shared memory when it fits (29-cycle loads in the ramp), else in HBM
+        double2* tab = (wp.N <= smemEntriesPerWarp)
+                           ? reinterpret_cast<double2*>(pairs_smem) + (size_t)(threadIdx.x >> 5) * smemEntriesPerWarp
+                           : tabs + tabOff[pid];
+        wp.pstore = (pbuf && (long long)wp.K + 1 <= pbufStrideK) ? pbuf + (size_t)pid * (size_t)pbufStrideK * 32 + lane : nullptr;
         // BuildModel (queueanalyzer.go:99-131): the table, cooperatively
         bool bad = false;
         for (int i = lane; i < wp.N; i += 32) {
@@ -362,7 +371,9 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         float ylo = 0.0f, yhi = 0.0f;                  // eval(lo), eval(hi): always known after the first round,
                                                        // so a midpoint that rounds onto an endpoint costs nothing
         bool first = true;
+        int rounds = 0;
         while (__any_sync(0xffffffffu, !done)) {
+            ++rounds;
             // --- choose this lane's evaluation point ---
             int node = 0; bool act = false; float x = 0.0f;
             if (!done) {
@@ -383,6 +394,8 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                 }
             }
             bool valid;
+            if (__any_sync(0xffffffffu, act)) ++activeRounds;
+            ++totalRounds;
             bool solved = warp_solve(wp, act, x, st, steps, valid);
             if (act) lastX = x;
             if (__any_sync(0xffffffffu, act && !solved)) { toSlow = true; break; }
@@ -431,6 +444,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
             }
             first = false;
         }
+        if (lane == 0) { atomicAdd(step_counter + 1, (unsigned long long)rounds); atomicMax(step_counter + 2, (unsigned long long)rounds); }
         if (toSlow) break;
         // results of the two bisections
         const bool failT = __shfl_sync(0xffffffffu, (int)failed, 0), failI = __shfl_sync(0xffffffffu, (int)failed, 16);
@@ -479,6 +493,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         const float cost = sys.acc_cost[a] * (float)totalNumInstances;
         const float rate2 = totalRate / (float)numReplicas;
         if (rate2 <= 0.0f || rate2 > wp.rateMax) break;                    // Analyze error -> nil
+        if (lane == 0) atomicAdd(step_counter + 3, (unsigned long long)((have == 0u ? 1 : 0) + ((rate2GuessOk && rate2 == rate2Guess) ? 0 : 100)));
         if (!(rate2GuessOk && rate2 == rate2Guess)) {
             // the guess missed: evaluate the real second rate
             SolveStats stl = st; bool v;
@@ -498,6 +513,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
 
     if (ok) rec.value = transition_penalty(sys.srv_cur_acc[s], sys.srv_cur_replicas[s], sys.srv_cur_cost[s], rec.acc,
                                            rec.numReplicas, rec.cost);
+    if (dbg && lane == 0) { dbg[2 * pid] = (unsigned long long)(clock64() - tStart); dbg[2 * pid + 1] = ((unsigned long long)totalRounds << 32) | (unsigned)activeRounds; }
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
     if (lane == 0) {
         if (toSlow) { ok = false; slow_list[atomicAdd(slow_count, 1)] = pid; }

@@ -69,7 +69,7 @@ def test_queue_size_matches_oracle(wva, oracle, ctx):
     assert (want[3] == 0).sum() > n // 4
 
 
-@pytest.mark.parametrize("warp_max", [0, 16384])
+@pytest.mark.parametrize("warp_max", [0, 1 << 22])
 @pytest.mark.parametrize("seed,S,A", [(21, 300, 4), (22, 64, 8)])
 def test_pairs_match_oracle(wva, oracle, ctx, seed, S, A, warp_max):
     """both pair kernels: one thread per pair (warp_max 0) and one warp per pair with speculative bisection"""
@@ -77,7 +77,7 @@ def test_pairs_match_oracle(wva, oracle, ctx, seed, S, A, warp_max):
     ctx.pairs_set_warp_max(warp_max)
     ctx.upload(img)
     got, gfe = ctx.analyze_pairs()
-    ctx.pairs_set_warp_max(16384)
+    ctx.pairs_set_warp_max(1 << 22)
     want, wfe, steps = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
     assert np.array_equal(gfe, wfe)
     _assert_allocs_equal(got, want)
@@ -111,13 +111,13 @@ def test_pairs_iteration_budget(wva, oracle, ctx):
     c1.perf_alpha[0], c1.perf_beta[0], c1.perf_gamma[0], c1.perf_delta[0] = 7.470, 0.044, 15.415, 0.000337
     c1.acc_cost[0] = 100.0; c1.srv_arrival_rpm[0] = 6000.0
     want, wfe, _ = oracle.analyze_pairs(c1)
-    for warp_max in (0, 16384):
-        ctx.pairs_set_warp_max(warp_max)
+    for warp_max, pstore in ((0, 0), (1 << 22, 0), (1 << 22, 1)):
+        ctx.pairs_set_warp_max(warp_max); ctx.pairs_set_pstore(pstore)
         ctx.upload(c1)
         got, gfe = ctx.analyze_pairs()
         assert np.array_equal(gfe, wfe) and got.num_replicas[0] == 3
         _assert_allocs_equal(got, want)
-    ctx.pairs_set_warp_max(16384)
+    ctx.pairs_set_warp_max(1 << 22); ctx.pairs_set_pstore(0)
 
 
 def test_pairs_overflow_rescale_path(wva, oracle, ctx):
