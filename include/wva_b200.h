@@ -230,6 +230,11 @@ int wva_pairs_fetch(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible);
  * wva_pairs_commit so that wva_solve may run the (sequential, replicated) greedy assignment. */
 int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
 int wva_pairs_commit(wva_ctx* ctx);
+/* Tuning: certified closed-form tails on/off.  Chains that would run a long
+ * constant-rate tail are first evaluated from the exact ramp plus the geometric closed form and accepted
+ * only when every float32 rounding of the result is unambiguous within a proven error bound; otherwise
+ * the exact chain runs.  Results are identical either way; default on. */
+int wva_set_certified_tails(wva_ctx* ctx, int32_t on);
 /* Tuning: shards with at most max_pairs (server, accelerator) pairs use the warp-per-pair kernel
  * (speculative bisection, lowest latency); larger shards use one thread per pair (highest
  * throughput).  Results do not depend on it.  Default 2^22 (measured: the warp kernel is ~30x faster than thread-per-pair even at 8 000 pairs
@@ -313,8 +318,8 @@ int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase);
  * on it or order other work after it). */
 void* wva_stream(const wva_ctx* ctx);
 /* Sweep tuning: candidates whose chain tail needs more than tail_cap steps are deferred from the
- * per-pair sweep kernel to a second kernel that groups chains of similar length (0 = never defer).
- * Results do not depend on it.  wva_grid_list_sizes: how many candidates the last sweep deferred /
+ * per-pair sweep kernel to a second kernel that groups chains of similar length (0 = never defer,
+ * negative = automatic: 0 when certified tails are on, 192 otherwise).  Results do not depend on it.  wva_grid_list_sizes: how many candidates the last sweep deferred /
  * sent to the materialised-p[] path. */
 int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap);
 int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal);

@@ -22,7 +22,7 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_pair_counters", "wva_pair_debug", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_analyze", "wva_pairs_fetch",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
         L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
         L.wva_pairs_set_warp_max.argtypes = [vp, i32]
         L.wva_pairs_set_pstore.argtypes = [vp, i32]
+        L.wva_set_certified_tails.argtypes = [vp, i32]
         L.wva_analyze.argtypes = [vp, i32, i32, i32]
         L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
         L.wva_grid_set_tail_cap.argtypes = [vp, i32]
@@ -150,6 +151,9 @@ class Context:
         v = (C.c_uint64 * 4)()
         self._ck(lib().wva_pair_counters(self._h, v))
         return dict(steps=v[0], rounds_sum=v[1], rounds_max=v[2], trailing=v[3])
+
+    def set_certified_tails(self, on):
+        self._ck(lib().wva_set_certified_tails(self._h, 1 if on else 0))
 
     def pair_debug(self):
         n = self.count * self.image.A

@@ -74,6 +74,7 @@ struct wva_ctx {
     int pairs_warp_max = 1 << 22;
     int pairs_pstore = 0;
     int pairs_smem = 1;
+    int certified = 1;
     int pairs_debug = 0;
     DevBuf pairDbg;
 
@@ -85,7 +86,7 @@ struct wva_ctx {
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
     DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch;
-    int grid_tail_cap = 192; int last_heavy = 0, last_slow = 0;
+    int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     int grid_r = 0, grid_b = 0; bool grid_valid = false;
     uint64_t grid_counters[3] = {0, 0, 0};
@@ -274,7 +275,7 @@ int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
     CK(cudaMemcpyAsync(ctx->arena.p, st, total, cudaMemcpyHostToDevice, ctx->stream));
     char* d = ctx->arena.as<char>();
     DevSystem& ds = ctx->dsys;
-    ds.S = S; ds.A = A; ds.M = M; ds.T = T;
+    ds.S = S; ds.A = A; ds.M = M; ds.T = T; ds.cert = ctx->certified;
     ds.acc_cost = (const float*)(d + o_acc_cost); ds.acc_multiplicity = (const int*)(d + o_acc_mult); ds.acc_type = (const int*)(d + o_acc_type);
     ds.type_capacity = (const long long*)(d + o_cap);
     ds.perf_alpha = (const float*)(d + o_pa); ds.perf_beta = (const float*)(d + o_pb); ds.perf_gamma = (const float*)(d + o_pg); ds.perf_delta = (const float*)(d + o_pd);
@@ -443,6 +444,12 @@ int wva_pairs_commit(wva_ctx* ctx) {
     ctx->pairs_complete = true;
     return WVA_OK;
 }
+int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
+    if (!ctx) return WVA_EINVAL;
+    ctx->certified = on ? 1 : 0;
+    ctx->dsys.cert = ctx->certified;
+    return WVA_OK;
+}
 int wva_pairs_set_pstore(wva_ctx* ctx, int32_t on) {
     if (!ctx) return WVA_EINVAL;
     ctx->pairs_pstore = (on & 1) ? 1 : 0;
@@ -531,7 +538,9 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     gp.keys = ctx->keys.as<unsigned long long>();
     gp.counters = ctx->counters.as<unsigned long long>();
     gp.pair_tab = ctx->pairTab.as<double2>();
-    gp.tail_cap = ctx->grid_tail_cap;
+    // with certified tails almost no chain runs a long exact tail any more: finishing the few that do
+    // inside the sweep kernel is cheaper than a second kernel + host round trip (cap < 0 = automatic)
+    gp.tail_cap = ctx->grid_tail_cap >= 0 ? ctx->grid_tail_cap : (ctx->certified ? 0 : 192);
     gp.slow_count = ctx->gridSlowCount.as<int>();
     gp.heavy_count = ctx->gridSlowCount.as<int>() + 1;
 
@@ -726,7 +735,7 @@ int wva_analyze_grid(wva_ctx* ctx, int32_t r_max, int32_t b_max, wva_grid_best* 
 }
 
 int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap) {
-    if (!ctx || tail_cap < 0) return WVA_EINVAL;
+    if (!ctx) return WVA_EINVAL;
     ctx->grid_tail_cap = tail_cap;
     return WVA_OK;
 }

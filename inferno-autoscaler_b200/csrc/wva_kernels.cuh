@@ -17,6 +17,7 @@ namespace wva {
 // Device copy of wva_system_soa (device pointers).
 struct DevSystem {
     int S, A, M, T;
+    int cert;      // tuning: certified closed-form tails on (1) / off (0); results identical either way
     const float* acc_cost; const int* acc_multiplicity; const int* acc_type;
     const long long* type_capacity;
     const float *perf_alpha, *perf_beta, *perf_gamma, *perf_delta;
@@ -123,6 +124,7 @@ __device__ bool create_allocation(const DevSystem& sys, int s, int a, double* sc
     sp.gamma = sys.perf_gamma[pi]; sp.delta = sys.perf_delta[pi];
     Analyzer qa;
     qa.build(sp, N, maxQueue, inTok, K, scratch);
+    qa.cert = sys.cert != 0;
     const float tTTFT = sys.srv_slo_ttft[s], tITL = sys.srv_slo_itl[s], tTPS = sys.srv_slo_tps[s];
     float rates[3], achieved[3];
     wva_metrics metrics;
@@ -248,6 +250,7 @@ __device__ __forceinline__ float bisect_node_x(float lo, float hi, int node) {
 struct WarpPair {
     ServFormula sv; ProvTableF pv;
     double* pstore;                 // this lane's column of the warp's chain-value buffer, or nullptr
+    bool cert;
     int N, K; long long inTok, outTok; bool tame;
     float rateMin, rateMax;
 };
@@ -256,7 +259,7 @@ struct WarpPair {
 // lane's chain needs the materialised path
 __device__ __forceinline__ bool warp_solve(const WarpPair& wp, bool active, float x, SolveStats& st, unsigned long long& steps,
                                            bool& valid) {
-    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active, wp.pstore);
+    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active, wp.pstore, wp.cert);
     valid = true;
     if (!active) return true;
     if (x < 0.0f) { valid = false; return true; }                       // queuemodel.go:31 (stale rho is in [0,1] < K)
@@ -333,6 +336,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         wp.sv.init(sp, inTok, Kt);
         wp.N = (int)N; wp.K = (int)(maxQueue + N); wp.inTok = inTok; wp.outTok = Kt;
         wp.tame = tame_parms(sp, inTok, Kt);
+        wp.cert = sys.cert != 0;
         // the table lives in shared memory when it fits (29-cycle loads in the ramp), else in HBM
         double2* tab = (wp.N <= smemEntriesPerWarp)
                            ? reinterpret_cast<double2*>(pairs_smem) + (size_t)(threadIdx.x >> 5) * smemEntriesPerWarp
@@ -601,6 +605,7 @@ struct GridServer {
     int curAcc, curRep; float curCost;
     float accCost; long long numInst;
     ServiceParms sp;
+    bool cert;
 };
 
 // QueueAnalyzer.Analyze (queueanalyzer.go:134-174) on a fresh analyzer with MaxBatchSize b,
@@ -620,7 +625,7 @@ __device__ __forceinline__ int analyze_table(const ServTable& tb, const GridServ
     if ((1.0f >= (float)K) || (lambda < 0.0f)) return WVA_CAND_ERR_MODEL;
     SolveStats st;
     ProvTable pv; pv.rateD = tb.rateD; pv.rcp = tb.rcp; pv.rateF_ = tb.rateF;
-    int rc = solve_fast(pv, b, K, lambda, tame, tailCap, st, steps, deferCost);
+    int rc = solve_fast(pv, b, K, lambda, tame, tailCap, st, steps, deferCost, gs.cert);
     if (rc == WVA_SOLVE_DEFER) return -2;                                 // long chain: heavy kernel
     if (rc == WVA_SOLVE_CAREFUL) rc = solve_stream_table(tb, b, K, lambda, tame, st, steps);
     if (rc != WVA_SOLVE_OK) return -1;                                    // literal path
@@ -665,6 +670,7 @@ __device__ __forceinline__ void load_grid_server(const DevSystem& sys, int s, in
     gs.curAcc = sys.srv_cur_acc[s]; gs.curRep = sys.srv_cur_replicas[s]; gs.curCost = sys.srv_cur_cost[s];
     gs.accCost = sys.acc_cost[a];
     gs.numInst = num_instances(sys, m, a);
+    gs.cert = sys.cert != 0;
 }
 
 // Block = one (server, accelerator) pair x one chunk of replica counts.  The pair's service-rate
@@ -769,7 +775,8 @@ k_grid(DevSystem sys, GridParams gp) {
         if (b > nGood) st = -1;
         else {
             // one call site: the second trip (cap 0) only happens when the deferred list is full
-            for (int cap = gp.tail_cap;; cap = 0) {
+            // short chains (K <= 1024) never leave this kernel: deferral only pays for long tails
+            for (int cap = (11 * b <= 1024) ? 0 : gp.tail_cap;; cap = 0) {
                 st = analyze_table(tb, gs, b, rate, tame, cap, m, rateTPS, steps, deferCost);
                 if (st != -2) break;
                 int k = atomicAdd(gp.heavy_count, 1);
@@ -838,7 +845,7 @@ __device__ int analyze_candidate(const DevSystem& sys, int s, int a, int r, int 
     load_grid_server(sys, s, a, gs);
     Analyzer qa;
     qa.build(gs.sp, b, (long long)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, gs.inTok, gs.outTok, scratch);
-    qa.tab = tab; qa.uni = true;
+    qa.tab = tab; qa.uni = true; qa.cert = sys.cert != 0;
     const float lamMaxBack = qa.rateMax / 1000.0f;
     rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
     rate = gs.totalRate / (float)r;

@@ -65,8 +65,20 @@ def test_config2_full_sweep_properties(wva, oracle, ctx):
     ctx.grid_set_tail_cap(64)
     best1, _, status1 = ctx.analyze_grid(R, B, want_cube=True)
     ctx.grid_set_tail_cap(192)
+    best2, _, status2 = ctx.analyze_grid(R, B, want_cube=True)
+    ctx.grid_set_tail_cap(-1)
+    assert best2.tobytes() == best.tobytes() and np.array_equal(status2, status)
     assert best0.tobytes() == best.tobytes() and cube0.tobytes() == cube.tobytes() and np.array_equal(status0, status)
     assert best1.tobytes() == best.tobytes() and np.array_equal(status1, status)
+    # certified closed-form tails are a pure speed-up: switching them off must not change one bit
+    ctx.set_certified_tails(False)
+    ctx.upload(img)
+    best_x, cube_x, status_x = ctx.analyze_grid(R, B, want_cube=True)
+    cnt_x = ctx.grid_counters()
+    ctx.set_certified_tails(True)
+    ctx.upload(img)
+    assert best_x.tobytes() == best.tobytes() and cube_x.tobytes() == cube.tobytes() and np.array_equal(status_x, status)
+    assert cnt["steps_executed"] < cnt_x["steps_executed"]
     # shard invariance: two shards concatenate to the full result
     half = img.S // 2
     ctx.set_shard(0, half); b0, _, _ = ctx.analyze_grid(R, B)
@@ -85,6 +97,13 @@ def test_config3_pairs_sample(wva, oracle, ctx):
     got_t, gfe_t = ctx.analyze_pairs()
     ctx.pairs_set_warp_max(1 << 22)
     assert np.array_equal(gfe, gfe_t) and got.equal_bits(got_t)[0]
+    ctx.set_certified_tails(False)
+    ctx.upload(img)
+    got_x, gfe_x = ctx.analyze_pairs()
+    ctx.set_certified_tails(True)
+    ctx.upload(img)
+    assert np.array_equal(gfe, gfe_x) and got.equal_bits(got_x)[0]
+    ctx.analyze_pairs(download=False)
     rng = np.random.default_rng(3)
     pick = np.sort(rng.choice(img.S, 40, replace=False))
     for s in pick:

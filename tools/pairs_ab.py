@@ -10,8 +10,8 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 img, c = wva.synth.baseline_config(cfg)
 ctx = binding.Context(0)
 ctx.upload(img)
-for name, warp_max, knob in [("warp+smem", 1 << 22, 0), ("warp+smem+pstore", 1 << 22, 1)]:
-    ctx.pairs_set_warp_max(warp_max); ctx.pairs_set_pstore(knob)
+for name, warp_max, knob, cert in [("warp certified", 1 << 22, 0, 1), ("warp exact", 1 << 22, 0, 0)]:
+    ctx.pairs_set_warp_max(warp_max); ctx.pairs_set_pstore(knob); ctx.set_certified_tails(cert); ctx.upload(img)
     ts = []
     for i in range(6):
         ctx.analyze_pairs(download=False)
