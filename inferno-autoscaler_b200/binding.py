@@ -153,7 +153,7 @@ class Context:
         return dict(steps=v[0], rounds_sum=v[1], rounds_max=v[2], trailing=v[3])
 
     def set_certified_tails(self, on):
-        self._ck(lib().wva_set_certified_tails(self._h, 1 if on else 0))
+        self._ck(lib().wva_set_certified_tails(self._h, int(on)))
 
     def pair_debug(self):
         n = self.count * self.image.A

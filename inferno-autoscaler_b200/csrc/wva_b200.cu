@@ -75,6 +75,7 @@ struct wva_ctx {
     int pairs_pstore = 0;
     int pairs_smem = 1;
     int certified = 1;
+    int grid_rows = 1;
     int pairs_debug = 0;
     DevBuf pairDbg;
 
@@ -446,7 +447,8 @@ int wva_pairs_commit(wva_ctx* ctx) {
 }
 int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
     if (!ctx) return WVA_EINVAL;
-    ctx->certified = on ? 1 : 0;
+    ctx->certified = (on & 1) ? 1 : 0;
+    ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : 1);      // bit 1: always one thread per candidate; bit 2: always one thread per row
     ctx->dsys.cert = ctx->certified;
     return WVA_OK;
 }
@@ -558,8 +560,15 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     int slow_cap = 1 << 16;
     CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
 
+    // certified tails on: one thread per (server, accelerator, replicas) row with a shared ramp (k_grid_rows);
+    // off: one thread per candidate (k_grid)
+    // (the row kernel needs >= 32 K rows to fill the machine: each thread walks its row's batch sizes serially)
+    const bool rowsMode = ctx->certified && ctx->grid_rows && (ctx->grid_rows == 2 || slicePairsMax * (size_t)r_max >= 32768);
     const size_t smem = (size_t)b_max * 20;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (slicePairsMax * (size_t)gp.n_rchunks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
     CK(ctx->blockSlot.ensure((slicePairsMax * (size_t)gp.n_rchunks + 1) * sizeof(GridSlot)));
     gp.block_slot = ctx->blockSlot.as<GridSlot>();
@@ -582,7 +591,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     for (int sBeg = 0; sBeg < ns; sBeg += srvPerSlice) {
         const int sCnt = (ns - sBeg) < srvPerSlice ? (ns - sBeg) : srvPerSlice;
         const size_t slicePairs = (size_t)sCnt * A;
-        const size_t nBlocks = slicePairs * (size_t)gp.n_rchunks;
+        const size_t nBlocks = rowsMode ? slicePairs : slicePairs * (size_t)gp.n_rchunks;
         gp.pair_base = sBeg * A;
         int counts[2] = {0, 0};
         int slow = 0, heavy = 0;
@@ -590,7 +599,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
             CK(cudaEventRecord(ctx->evk0, ctx->gstream));
-            k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
+            if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
+            else k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
             CK(cudaEventRecord(ctx->evk1, ctx->gstream));
             CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->gstream));
@@ -607,15 +617,18 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
                 // long chains: order by estimated length (longest first), one thread per chain
                 int* hist = ctx->heavyHist.as<int>();
                 CK(cudaEventRecord(ctx->evh0, ctx->gstream));
-                CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->gstream));
-                k_heavy_hist<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist);
-                LAUNCH_CHECK();
-                k_heavy_prefix<<<1, 256, 0, ctx->gstream>>>(hist);
-                LAUNCH_CHECK();
-                k_heavy_scatter<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist, ctx->heavyOrder.as<int>());
-                LAUNCH_CHECK();
-                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, ctx->heavyOrder.as<int>(), heavy,
-                                                                        nullptr, 0, 0);
+                const int* order = nullptr;
+                if (heavy >= 4096) {                  // a short list fits in one wave: ordering it buys nothing
+                    CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->gstream));
+                    k_heavy_hist<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist);
+                    LAUNCH_CHECK();
+                    k_heavy_prefix<<<1, 256, 0, ctx->gstream>>>(hist);
+                    LAUNCH_CHECK();
+                    k_heavy_scatter<<<(heavy + 255) / 256, 256, 0, ctx->gstream>>>(gp.heavy_cost, heavy, hist, ctx->heavyOrder.as<int>());
+                    LAUNCH_CHECK();
+                    order = ctx->heavyOrder.as<int>();
+                }
+                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, order, heavy, nullptr, 0, 0);
                 LAUNCH_CHECK();
                 CK(cudaEventRecord(ctx->evh1, ctx->gstream));
                 CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->gstream));

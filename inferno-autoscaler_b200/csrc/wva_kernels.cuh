@@ -256,13 +256,16 @@ struct WarpPair {
 };
 
 // one evaluation per lane (EvalTTFT / EvalITL / Analyze share the Solve); returns false when the
-// lane's chain needs the materialised path
+// lane's chain needs the materialised path.  certOnly: a speculative evaluation — if the certified tail
+// cannot decide, report `uncertain` instead of running the long exact tail (the caller re-evaluates the
+// node exactly only if the bisection actually walks through it).
 __device__ __forceinline__ bool warp_solve(const WarpPair& wp, bool active, float x, SolveStats& st, unsigned long long& steps,
-                                           bool& valid) {
-    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active, wp.pstore, wp.cert);
-    valid = true;
+                                           bool& valid, bool certOnly, bool& uncertain) {
+    int rc = solve_uni(wp.pv, wp.N, wp.K, x, wp.tame, st, steps, active, wp.pstore, wp.cert, certOnly);
+    valid = true; uncertain = false;
     if (!active) return true;
     if (x < 0.0f) { valid = false; return true; }                       // queuemodel.go:31 (stale rho is in [0,1] < K)
+    if (rc == WVA_SOLVE_UNCERTAIN) { uncertain = true; return true; }
     if (rc == WVA_SOLVE_CAREFUL) rc = solve_stream(wp.sv, (long long)wp.N, (long long)wp.K, x, wp.tame, st, steps);
     return rc == WVA_SOLVE_OK;
 }
@@ -397,13 +400,14 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                     if (xm == l2 || xm == h2) act = false;      // resolved from the memo while walking
                 }
             }
-            bool valid;
+            bool valid, unc;
             if (__any_sync(0xffffffffu, act)) ++activeRounds;
             ++totalRounds;
-            bool solved = warp_solve(wp, act, x, st, steps, valid);
-            if (act) lastX = x;
+            // tree nodes are speculative (certOnly); the two boundary evaluations are needed for sure
+            bool solved = warp_solve(wp, act, x, st, steps, valid, node > 0, unc);
+            if (act && !unc) lastX = x;
             if (__any_sync(0xffffffffu, act && !solved)) { toSlow = true; break; }
-            const float y = act && valid ? eval_y(wp, half, st) : 0.0f;
+            float y = act && valid && !unc ? eval_y(wp, half, st) : 0.0f;
             // --- walk the realised path (uniform inside each half-warp) ---
             if (first) {
                 const float yb0 = __shfl_sync(0xffffffffu, y, base + 0), yb1 = __shfl_sync(0xffffffffu, y, base + 1);
@@ -423,28 +427,47 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
             }
             {
                 const int levels = first ? 3 : 4;
-                int cur = 1;
-                for (int l = 0; l < levels; ++l) {
-                    const int src = base + (first ? cur + 1 : cur);
-                    float ys = __shfl_sync(0xffffffffu, y, src);
-                    bool vs = __shfl_sync(0xffffffffu, (int)valid, src);
-                    if (!done) {
-                        if (iters == WVA_BISECT_MAXIT) { done = true; }
-                        else {
-                            const float xs = 0.5f * (lo + hi);
-                            if (xs == lo) { ys = ylo; vs = true; } else if (xs == hi) { ys = yhi; vs = true; }
-                            ++iters;
-                            if (!vs) { failed = true; done = true; }
+                int cur = 1, lvl = 0;
+                bool slowExit = false;
+                for (;;) {
+                    bool pend = false;                 // this half-warp walked into a node whose speculative evaluation was uncertain
+                    for (int l = 0; l < levels; ++l) {
+                        const int src = base + (first ? cur + 1 : cur);
+                        float ys = __shfl_sync(0xffffffffu, y, src);
+                        bool vs = __shfl_sync(0xffffffffu, (int)valid, src);
+                        const bool us = __shfl_sync(0xffffffffu, (int)unc, src);
+                        if (!done && !pend && l == lvl) {
+                            if (iters == WVA_BISECT_MAXIT) { done = true; }
                             else {
-                                xStar = xs;
-                                if (within_tolerance(ys, target, WVA_BISECT_TOL)) done = true;
-                                else if ((inc && target < ys) || (!inc && target > ys)) { hi = xs; yhi = ys; cur = 2 * cur; }
-                                else { lo = xs; ylo = ys; cur = 2 * cur + 1; }
-                                if (!done && iters == WVA_BISECT_MAXIT) done = true;
+                                const float xs = 0.5f * (lo + hi);
+                                bool known = true;
+                                if (xs == lo) { ys = ylo; vs = true; } else if (xs == hi) { ys = yhi; vs = true; }
+                                else if (us) known = false;
+                                if (!known) pend = true;           // needs the exact chain: evaluated below, then the walk resumes here
+                                else {
+                                    ++iters; ++lvl;
+                                    if (!vs) { failed = true; done = true; }
+                                    else {
+                                        xStar = xs;
+                                        if (within_tolerance(ys, target, WVA_BISECT_TOL)) done = true;
+                                        else if ((inc && target < ys) || (!inc && target > ys)) { hi = xs; yhi = ys; cur = 2 * cur; }
+                                        else { lo = xs; ylo = ys; cur = 2 * cur + 1; }
+                                        if (!done && iters == WVA_BISECT_MAXIT) done = true;
+                                    }
+                                }
                             }
                         }
                     }
+                    if (!__any_sync(0xffffffffu, pend)) break;
+                    // exact evaluation of the pending node(s): the lane that owns node `cur` of a pending half-warp
+                    const bool mine = pend && (hl == (first ? cur + 1 : cur));
+                    bool v2, u2;
+                    ++activeRounds;
+                    bool solved2 = warp_solve(wp, mine, x, st, steps, v2, false, u2);
+                    if (__any_sync(0xffffffffu, mine && !solved2)) { slowExit = true; break; }
+                    if (mine) { valid = v2; unc = false; lastX = x; y = v2 ? eval_y(wp, half, st) : 0.0f; }
                 }
+                if (slowExit) { toSlow = true; break; }
             }
             first = false;
         }
@@ -482,7 +505,8 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
             const bool actA = (lane == 0) && needX1, actB = (lane == 1) && rate2GuessOk;
             SolveStats stl = st;
             bool v;
-            solved = warp_solve(wp, actA || actB, lane == 0 ? x1 : rate2Guess / 1000.0f, stl, steps, v);
+            bool uu;
+            solved = warp_solve(wp, actA || actB, lane == 0 ? x1 : rate2Guess / 1000.0f, stl, steps, v, false, uu);
             if (__any_sync(0xffffffffu, (actA || actB) && !solved)) { toSlow = true; break; }
             if (needX1) { st1 = shfl_stats(stl, 0); valid1 = __shfl_sync(0xffffffffu, (int)v, 0); }
             else { st1 = shfl_stats(st, __ffs(have) - 1); valid1 = true; }
@@ -501,7 +525,8 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
         if (!(rate2GuessOk && rate2 == rate2Guess)) {
             // the guess missed: evaluate the real second rate
             SolveStats stl = st; bool v;
-            solved = warp_solve(wp, lane == 0, rate2 / 1000.0f, stl, steps, v);
+            bool uu;
+            solved = warp_solve(wp, lane == 0, rate2 / 1000.0f, stl, steps, v, false, uu);
             if (__any_sync(0xffffffffu, lane == 0 && !solved)) { toSlow = true; break; }
             st2 = shfl_stats(stl, 0); valid2 = __shfl_sync(0xffffffffu, (int)v, 0);
         }
@@ -825,6 +850,252 @@ k_grid(DevSystem sys, GridParams gp) {
     __syncthreads();
     const unsigned long long blockKey = sh_key;
     if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {          // keys are unique per candidate: one owner
+        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
+        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
+        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        gp.block_slot[blockIdx.x] = sl_;
+        atomicMin(&gp.keys[sl], blockKey);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_grid_rows: the sweep with ONE THREAD PER ROW (server, accelerator, replicas).
+//
+// All candidates of a row share lambda = totalRate / r, and the chain of batch size b uses
+// servRate[min(n, b-1)]: its first b steps are the first b steps of the chain of every larger batch
+// size.  So a row needs ONE ramp p[1..B]; candidate b is evaluated at the moment the ramp reaches state b,
+// from (p[b], sum_{i<=b} p[i], sum_{i<=b} i p[i]) and the certified closed-form tail (cert_eval) — O(1) per
+// candidate instead of O(b) + tail.  When the ramp itself dies out (p[n] below 2^-68 of every aggregate
+// with all later ratios <= 0.998), the remaining candidates of the row share the frozen sums.
+// A candidate whose certificate fails (ambiguous float32 rounding, ill-conditioned closed form, value
+// window left) is appended to the deferred list and evaluated by the exact chain in k_grid_list.
+// Lanes of a warp hold consecutive r of the same pair: they step n together, so the shared-memory
+// table reads are broadcasts.
+// ---------------------------------------------------------------------------------------
+#define WVA_ROWS_THREADS 64
+__global__ void __launch_bounds__(WVA_ROWS_THREADS)
+k_grid_rows(DevSystem sys, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* rateD = reinterpret_cast<double*>(smem_raw);
+    double* rcp = rateD + gp.b_max;
+    float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
+    __shared__ int sh_nGood;
+    __shared__ unsigned long long sh_key;
+    __shared__ unsigned long long sh_cnt[3];
+
+    const int pairSlice = blockIdx.x;
+    const int pairLocal = gp.pair_base + pairSlice;
+    const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
+    const int s = gp.s0 + sl;
+    const int B = gp.b_max, R = gp.r_max;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
+        gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
+    }
+    const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
+    GridServer gs;
+    int blockStatus = WVA_CAND_OK;
+    if (!pairOk) blockStatus = WVA_CAND_ERR_PAIR;
+    else {
+        load_grid_server(sys, s, a, gs);
+        if (gs.inTok < 0 || gs.outTok < 1 || gs.sloTTFT < 0.0f || gs.sloITL < 0.0f || gs.sloTPS < 0.0f)
+            blockStatus = WVA_CAND_ERR_CONFIG;
+    }
+    const size_t candBase = ((size_t)pairLocal * R) * (size_t)B;
+    if (blockStatus != WVA_CAND_OK) {
+        if (gp.status || gp.cube) {
+            const size_t n = (size_t)R * B;
+            for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+                if (gp.status) gp.status[candBase + i] = (unsigned char)blockStatus;
+                if (gp.cube) { float4 z = make_float4(0, 0, 0, 0); float4* c = reinterpret_cast<float4*>(&gp.cube[candBase + i]); c[0] = z; c[1] = z; }
+            }
+        }
+        return;
+    }
+    __syncthreads();
+    ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
+    double2* gtab = gp.pair_tab + (size_t)pairSlice * B;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        float r = sf.rate(i + 1);
+        rateF[i] = r;
+        double d = (double)r;
+        double y = rcp_refined(d);
+        rateD[i] = d; rcp[i] = y;
+        gtab[i] = make_double2(d, y);
+        if (!(r > 0.0f) || !(r < CUDART_INF_F)) atomicMin(&sh_nGood, i);
+    }
+    const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
+    __syncthreads();
+    const int nGood = sh_nGood;
+
+    unsigned long long bestKey = WVA_KEY_NONE;
+    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    unsigned long long steps = 0, algSteps = 0, okCount = 0;
+
+    for (int r = threadIdx.x + 1; r <= R; r += blockDim.x) {
+        const float rate = gs.totalRate / (float)r;
+        const float lambda = rate / 1000.0f;
+        double lam = (double)lambda;
+        const bool lamOk = (lam >= 0x1p-100 && lam <= 0x1p20);
+        lam = pin(lam);
+        const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
+        value = value + 0.0f;
+        // shared ramp state
+        double p = 1.0, sum = 1.0, uN = 0.0, dn = 0.0;
+        double exInSys = 0.0, exSumP = 0.0;     // exact normalised sums of a stopped row
+        unsigned thrHi = 0u, hmin = 0x3ff00000u;
+        bool stopped = false;        // ramp died out: sums frozen
+        bool broken = !lamOk;        // chain left the value window (or bad table entry): rest of the row goes to the exact kernels
+        const size_t rowBase = candBase + (size_t)(r - 1) * B;
+        for (int n = 0; n < B; ++n) {
+            const int b = n + 1;
+            // ---- one step of the shared ramp: state b ----
+            if (!stopped && !broken) {
+                if (b > nGood) broken = true;
+                else {
+                    const double t = p * lam;
+                    const double pn = div_core(t, rateD[n], rcp[n]);
+                    const unsigned hq = (unsigned)__double2hiint(pn);
+                    if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) broken = true;
+                    else {
+                        sum += pn; dn += 1.0; uN += dn * pn; p = pn;
+                        ++steps;
+                        if (n == 0 && pn >= 0x1p-400)      // 2^-68 min(1,p1) / K_max: the neglected mass is < 2^-58 of every aggregate
+                            thrHi = (unsigned)__double2hiint((0x1p-68 * fmin(1.0, pn)) / (double)(11 * B));
+                        hmin = hq < hmin ? hq : hmin;
+                        if (hq < thrHi && tame && lambda <= 0.998f * rateF[n] && sum <= 0x1p400) {
+                            // The chain has died out (solve_stream's truncation rule with a 2^10 stricter threshold):
+                            // every candidate b >= this state sees the SAME normalised prefix, exactly.  Run the
+                            // reference's second pass once for the row (mm1modelstatedependent.go:49-55 up to here).
+                            stopped = true;
+                            const double S = sum;
+                            if ((int)(hmin >> 20) - (int)((unsigned)__double2hiint(S) >> 20) < -1000) broken = true;
+                            else {
+                                const double yS = rcp_refined(S);
+                                double q = div_core(1.0, S, yS), pp = 1.0, di = 0.0;
+                                exSumP = q; exInSys = 0.0;
+                                for (int i = 1; i <= b; ++i) {
+                                    pp = div_core(pp * lam, rateD[i - 1], rcp[i - 1]);
+                                    q = div_core(pp, S, yS);
+                                    di += 1.0;
+                                    exInSys += di * q;
+                                    exSumP += q;
+                                }
+                                steps += (unsigned long long)b;
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- candidate (r, b) ----
+            const size_t ci = rowBase + (size_t)n;
+            const int K = 11 * b;
+            const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
+            const float rateMax = lambdaMax * 1000.0f;
+            int st;
+            bool feasible = false;
+            wva_metrics m;
+            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            if (b > nGood) {                                   // bad table entry: literal path decides
+                int k = atomicAdd(gp.slow_count, 1);
+                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+                continue;
+            }
+            if (rate <= 0.0f) st = WVA_CAND_ERR_RATE_LE0;
+            else if (rate > rateMax) st = WVA_CAND_ERR_RATE_MAX;
+            else if (lambda < 0.0f) st = WVA_CAND_ERR_MODEL;
+            else {
+                SolveStats so;
+                bool certified = false;
+                if (!broken) {
+                    if (stopped) {
+                        // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no
+                        // longer change; float32(p[K]) < 2^-58 so throughput == lambda
+                        const double inServ = exInSys + (1.0 - exSumP) * (double)b;
+                        finish_stats(so, lambda, inServ, exInSys, 0.0f);
+                        certified = true;
+                    } else {
+                        CertIn c; c.pN = p; c.sumRamp = sum; c.uN = uN; c.lam = lam; c.sTail = rateD[n]; c.N = b; c.K = K; c.lambda = lambda;
+                        certified = cert_eval(c, false, so);
+                    }
+                }
+                if (!certified) {
+                    // exact chain in k_grid_list; when that list is full, right here
+                    int k = atomicAdd(gp.heavy_count, 1);
+                    if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)ci; gp.heavy_cost[k] = (float)K; continue; }
+                    ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
+                    float rt, dc;
+                    int st2 = analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
+                    if (st2 < 0) { int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)ci; continue; }
+                    so.avgServTime = 0.0f;      // metrics already final in m
+                    st = st2;
+                    goto have_metrics;
+                }
+                st = WVA_CAND_OK;
+                {
+                    const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+                    float rho = so.avgNumInServers / (float)b;
+                    rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+                    m.throughput = so.throughput * 1000.0f;
+                    m.avg_resp_time = so.avgRespTime;
+                    m.avg_wait_time = so.avgWaitTime;
+                    m.avg_num_in_serv = so.avgNumInServers;
+                    m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
+                    m.avg_token_time = decode_time(gs.sp, effConc);
+                    m.max_rate = rateMax;
+                    m.rho = rho;
+                }
+            have_metrics:
+                if (st != WVA_CAND_OK) {
+                    m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                    m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+                    goto write_out;
+                }
+                okCount++;
+                algSteps += 2ULL * (unsigned long long)(K + 1);
+                const float lamMaxBack = rateMax / 1000.0f;
+                const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+                const float ttft = m.avg_wait_time + m.avg_prefill_time;
+                const float itl = m.avg_token_time;
+                feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
+                           (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && (r >= gs.minReplicas);
+                if (feasible && value == value) {              // a NaN value is never selected
+                    const unsigned long long key = make_key(value, a, r, b);
+                    if (key < bestKey) { bestKey = key; bestItl = itl; bestTtft = ttft; bestRho = m.rho; }
+                }
+            }
+        write_out:
+            if (gp.cube) {
+                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+            }
+            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+        }
+    }
+    // ---- block argmin + counters ------------------------------------------------------------------
+    unsigned long long warpKey = bestKey;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
+        if (other < warpKey) warpKey = other;
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
+        okCount += __shfl_down_sync(0xffffffffu, okCount, o);
+    }
+    if (lane == 0) {
+        if (warpKey != WVA_KEY_NONE) atomicMin(&sh_key, warpKey);
+        atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
+    }
+    __syncthreads();
+    const unsigned long long blockKey = sh_key;
+    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {
         GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
         const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
         sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);

@@ -75,9 +75,17 @@ def test_config2_full_sweep_properties(wva, oracle, ctx):
     ctx.upload(img)
     best_x, cube_x, status_x = ctx.analyze_grid(R, B, want_cube=True)
     cnt_x = ctx.grid_counters()
+    ctx.set_certified_tails(3)          # certified tails, one thread per candidate
+    ctx.upload(img)
+    best_y, cube_y, status_y = ctx.analyze_grid(R, B, want_cube=True)
+    ctx.set_certified_tails(5)          # certified tails, one thread per row (shared ramp)
+    ctx.upload(img)
+    best_z, cube_z, status_z = ctx.analyze_grid(R, B, want_cube=True)
     ctx.set_certified_tails(True)
     ctx.upload(img)
     assert best_x.tobytes() == best.tobytes() and cube_x.tobytes() == cube.tobytes() and np.array_equal(status_x, status)
+    assert best_y.tobytes() == best.tobytes() and cube_y.tobytes() == cube.tobytes() and np.array_equal(status_y, status)
+    assert best_z.tobytes() == best.tobytes() and cube_z.tobytes() == cube.tobytes() and np.array_equal(status_z, status)
     assert cnt["steps_executed"] < cnt_x["steps_executed"]
     # shard invariance: two shards concatenate to the full result
     half = img.S // 2
