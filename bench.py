@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--servers-per-rank", type=int, default=None)
     ap.add_argument("--ref-servers", type=int, default=4, help="servers per step of the CPU arms' bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--limited", action="store_true",
+                    help="capacity-constrained assignment (SolveGreedy, PriorityExhaustive): capacities = 60 %% of the "
+                         "unconstrained demand; multi-GPU ranks gather the candidate rows and solve redundantly")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -190,8 +193,28 @@ def main():
     cand_rank = per_rank * img.A * R * B
     cand_total = cand_rank * world
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    # the metric cube (33 B per candidate) is materialised in HBM when it fits comfortably
+    want_cube = cand_rank * 33 <= 24 * (1 << 30)
+    rows_mode = per_rank * img.A * R >= 32768
+
+    from inferno_autoscaler_b200 import distributed as D
+    dev = torch.device("cuda", local_rank)
+    if args.limited:
+        # capacities that bind: 60 % of the demand of an unconstrained solve, computed once, untimed
+        ctx.upload(img)
+        ctx.analyze_pairs(download=False)
+        acc0, ch0 = ctx.solve(unlimited=True)
+        wva.synth.set_capacity_from_demand(img, ch0.acc, ch0.num_replicas, fraction=0.6)
 
     totals_t = None
+
+    def solve_step(download):
+        if not args.limited:
+            return ctx.solve(unlimited=True, download=download)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                D.gather_pair_rows_device(ctx, img.S, img.A, world, dev)
+        return ctx.solve(unlimited=False, policy=abi.POLICY_PRIORITY_EXHAUSTIVE, download=download)
 
     def allreduce_totals():
         """the one collective of the path: per-type {count, cost} partials summed over ranks (NCCL)."""
@@ -212,8 +235,8 @@ def main():
 
     def step_device():
         """hot path with the image resident in HBM; decisions stay in HBM."""
-        ctx.analyze(R, B, want_cube=True)            # Server.Calculate for all pairs || candidate sweep
-        ctx.solve(unlimited=True, download=False)
+        ctx.analyze(R, B, want_cube=want_cube)       # Server.Calculate for all pairs || candidate sweep
+        solve_step(False)
         ctx.allocate_by_type()
         allreduce_totals()
 
@@ -224,7 +247,7 @@ def main():
         ctx.analyze(R, B, want_cube=False)
         pairs = ctx.pairs_fetch()
         best = ctx.grid_fetch()
-        chosen = ctx.solve(unlimited=True)
+        chosen = solve_step(True)
         tot = ctx.allocate_by_type()
         allreduce_totals()
         return pairs, best, chosen, tot
@@ -291,12 +314,12 @@ def main():
     if rank == 0:
         hbm_peak, peak_src, peaks = load_peaks()
         k_us = float(np.mean(grid_kernel_us))
-        bytes_per_cand = 33.0                                     # 32 B AnalysisMetrics + 1 status byte, cube materialised
-        alg_bytes = bytes_per_cand * cand_rank + 88.0 * per_rank * img.A
+        bytes_per_cand = 33.0 if want_cube else 0.0               # 32 B AnalysisMetrics + 1 status byte when the cube is materialised
+        alg_bytes = bytes_per_cand * cand_rank + 88.0 * per_rank * img.A + 32.0 * per_rank
         achieved = alg_bytes / (k_us * 1e-6) / 1e9
-        # FP64 view: chain-state updates executed; one update = 5 FP64-pipe instructions in pass 1
-        # and 11 in pass 2 (DESIGN.md "k_grid"), i.e. 8 per counted step on average
-        fp64_ops = counters["steps_executed"] * 8.0
+        # FP64 view (estimate; the measured figure is ncu's sm__inst_executed_pipe_fp64 in profiles/): a chain-state
+        # update is ~8 FP64-pipe instructions, a certified closed-form tail (exp, log1p, 5 divisions) ~150
+        fp64_ops = counters["steps_executed"] * 8.0 + counters["candidates_ok"] * 150.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,15 +327,17 @@ def main():
             "config": {"workload": "BASELINE config %d: %d servers/GPU x %d accel x replicas 1-%d x batch 1-%d (+ %d Server.Calculate pairs, unlimited solve, per-type totals)"
                        % (args.config, per_rank, img.A, R, B, per_rank * img.A),
                        "candidates_per_step": cand_total, "pairs_per_step": per_rank * img.A * world,
-                       "l2": "flushed between timed iterations (256 MB write)", "cube": "materialised in HBM (33 B/candidate)"},
+                       "l2": "flushed between timed iterations (256 MB write)",
+                       "cube": "materialised in HBM (33 B/candidate)" if want_cube else "not materialised (winners only)",
+                       "assignment": "greedy, capacity caps at 60% of demand, PriorityExhaustive" if args.limited else "unlimited"},
             "clocks": clocks,
             "e2e": {"value": cand_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_grid + k_grid_list (sweep: per-pair kernel + deferred long chains)", "kernel_us": k_us,
+                         "traffic": None, "peak_source": peak_src, "kernel": ("k_grid_rows" if rows_mode else "k_grid") + " (+ k_grid_list for uncertified chains)", "kernel_us": k_us,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "the sweep is FP64-issue bound (see fp64); HBM fraction reported because BASELINE.json asks for it"},
+                         "note": "the sweep is FP64/issue bound, not HBM bound (see fp64); HBM fraction reported because BASELINE.json asks for it"},
             "fp64": {"chain_steps_executed": counters["steps_executed"], "chain_steps_reference": counters["steps_algorithmic"],
                      "truncation_ratio": counters["steps_algorithmic"] / max(1, counters["steps_executed"]),
                      "fp64_inst_per_s": fp64_ops / (k_us * 1e-6), "candidates_analysed": counters["candidates_ok"],

@@ -1023,7 +1023,7 @@ k_grid_rows(DevSystem sys, GridParams gp) {
                         certified = true;
                     } else {
                         CertIn c; c.pN = p; c.sumRamp = sum; c.uN = uN; c.lam = lam; c.sTail = rateD[n]; c.N = b; c.K = K; c.lambda = lambda;
-                        certified = cert_eval(c, false, so);
+                        certified = cert_eval(c, so);
                     }
                 }
                 if (!certified) {
