@@ -4,7 +4,7 @@
 One "step" = one reconcile pass over the workload: system upload, Server.Calculate for every
 (server, accelerator) pair (wva_analyze_pairs), the (server x accelerator x replicas x batch)
 candidate sweep with per-server argmin (wva_analyze_grid), the assignment (wva_solve) and the
-per-type totals (wva_allocate_by_type, + one NCCL all-reduce when N > 1).
+per-type totals (wva_allocate_by_type, + one NCCL all-gather and a rank-order sum when N > 1).
 
   value : whole-job candidates/s with the system image already resident in HBM (device timed,
           CUDA events on the library's stream, max over ranks)
@@ -147,10 +147,30 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Keep stdout for the one JSON line: anything a library prints there (NCCL's version banner, ...)
+    goes to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -217,21 +237,13 @@ def main():
         return ctx.solve(unlimited=False, policy=abi.POLICY_PRIORITY_EXHAUSTIVE, download=download)
 
     def allreduce_totals():
-        """the one collective of the path: per-type {count, cost} partials summed over ranks (NCCL)."""
+        """the one collective of the path: all-gather of the per-type {count, cost} partials (NCCL) + rank-order sum."""
         nonlocal totals_t
         if world == 1:
             return
-        ptr, nbytes = ctx.type_totals_device()
-        T = img.T
         if totals_t is None:
-            class _Arr:   # __cuda_array_interface__ view of the library's device buffer
-                def __init__(self, p, n, typestr):
-                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 3}
-            cnt = torch.as_tensor(_Arr(ptr, T, "<i8"), device="cuda")
-            cst = torch.as_tensor(_Arr(ptr + 8 * T, T, "<f4"), device="cuda")
-            totals_t = (cnt, cst)
-        with torch.cuda.stream(stream):
-            dist.all_reduce(totals_t[0]); dist.all_reduce(totals_t[1])
+            totals_t = D.TotalsExchange(ctx, img.T, dev, stream)
+        totals_t(sync=False)
 
     def step_device():
         """hot path with the image resident in HBM; decisions stay in HBM."""
@@ -270,7 +282,7 @@ def main():
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         l2_flush.fill_(i & 0xff)                      # evict L2 between timed iterations (not timed)
-        torch.cuda.synchronize()
+        barrier()                                     # ranks start every timed step together (not timed)
         ev[i][0].record(stream)
         step_device()
         ev[i][1].record(stream)
@@ -359,7 +371,7 @@ def main():
             cand = n_srv * img.A * R * B
             line["cpu_baseline"] = {"value": cand / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d of %d servers (%d candidates + %d pairs), %.1f s" % (n_srv, per_rank, cand, n_srv * img.A, dt)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -267,6 +267,17 @@ int wva_pair_debug(wva_ctx* ctx, uint64_t* out, int32_t n_pairs);
 int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec,
               int32_t* chosen_acc, wva_alloc_soa* chosen);
 
+/* Tuning (limited-capacity solve): 1 (default) = sort the S*A queue states once and run the
+ * sequential pass on a rank bitmap in shared memory; 0 = always the heap kernel.  The library itself
+ * falls back to the heap when the bitmap does not fit shared memory (more than ~1.7 M states).
+ * Same results either way.  wva_solve_greedy_path reports what the last limited solve ran:
+ * 1 heap, 2 ranked queue, 0 none yet. */
+int wva_solve_set_ranked(wva_ctx* ctx, int32_t on);
+int wva_solve_greedy_path(const wva_ctx* ctx);
+/* Instrumentation of the last ranked-queue solve: {queue pops, placements that did not fit,
+ * SM cycles in the queue loop, SM cycles in bestEffort}. */
+int wva_solve_stats(wva_ctx* ctx, uint64_t out[4]);
+
 /* Replaces System.AllocateByType (pkg/core/system.go:271-300): per accelerator type
  * count += replicas*numInstances*multiplicity, cost += alloc.cost over this rank's shard.
  * The sums are left in a device buffer (wva_type_totals_device) so the host can run the
@@ -277,6 +288,12 @@ int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost);
  * wva_allocate_by_type: count at ptr, cost at ptr + 8*T bytes.  The device sum uses a
  * fixed order (ascending server index) — Go sums in random map order (system.go:273,297). */
 int wva_type_totals_device(wva_ctx* ctx, void** dev_ptr, size_t* bytes);
+
+/* Sharded runs: the exchange step of the path.  Every rank all-gathers its 12*T-byte totals block
+ * (ONE collective); this call then sums the n_ranks gathered blocks (device memory, rank-major) in
+ * rank order into the totals buffer -- one launch, and unlike a ring/tree all-reduce the float32
+ * cost sums come out the same on every rank and every run. */
+int wva_type_totals_merge(wva_ctx* ctx, const void* gathered_dev, int32_t n_ranks);
 
 /* optimizer.SolutionTimeMsec (pkg/solver/optimizer.go:30-34): device+host time of the
  * last wva_solve in microseconds. */

@@ -22,7 +22,7 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_pair_counters", "wva_pair_debug", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch",
 ]
 
 
@@ -73,6 +73,10 @@ def lib():
         L.wva_selftest_division.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
         L.wva_pairs_set_warp_max.argtypes = [vp, i32]
         L.wva_pairs_set_pstore.argtypes = [vp, i32]
+        L.wva_solve_set_ranked.argtypes = [vp, i32]
+        L.wva_solve_greedy_path.argtypes = [vp]
+        L.wva_solve_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.wva_type_totals_merge.argtypes = [vp, C.c_void_p, i32]
         L.wva_set_certified_tails.argtypes = [vp, i32]
         L.wva_analyze.argtypes = [vp, i32, i32, i32]
         L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
@@ -163,6 +167,20 @@ class Context:
 
     def pairs_set_pstore(self, on):
         self._ck(lib().wva_pairs_set_pstore(self._h, int(on)))
+
+    def solve_set_ranked(self, on):
+        self._ck(lib().wva_solve_set_ranked(self._h, int(on)))
+
+    def type_totals_merge(self, gathered_ptr, n_ranks):
+        self._ck(lib().wva_type_totals_merge(self._h, C.c_void_p(int(gathered_ptr)), int(n_ranks)))
+
+    def solve_stats(self):
+        v = (C.c_uint64 * 4)()
+        self._ck(lib().wva_solve_stats(self._h, v))
+        return [int(x) for x in v]
+
+    def solve_greedy_path(self):
+        return int(lib().wva_solve_greedy_path(self._h))
 
     def pairs_set_warp_max(self, n):
         self._ck(lib().wva_pairs_set_warp_max(self._h, int(n)))

@@ -18,6 +18,10 @@ namespace {
 
 std::string g_create_error;
 
+// dynamic shared memory of k_greedy_solve / k_greedy_solve_ranked: 11264 heap entries of 20 bytes,
+// or the rank bitmap of 1.7 M states
+constexpr int kGreedySmem = 220 * 1024;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -83,6 +87,11 @@ struct wva_ctx {
     DevBuf chosenBuf; DevAllocs chosen{}; int* chosen_acc = nullptr; bool solved = false;
     DevBuf totals;
     DevBuf greedyBuf;
+    bool greedy_attr = false;
+    int greedy_ranked = 1;      // 0: always the heap kernel
+    int greedy_path = 0;        // last limited solve: 1 heap, 2 ranked queue
+    uint64_t greedy_stats[4] = {0, 0, 0, 0};
+    unsigned long long* greedy_stats_dev = nullptr;
 
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
@@ -786,36 +795,104 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
         if (!ctx->pairs_complete)
             return fail(ctx, WVA_ESTATE, "limited-capacity solve needs the candidates of every server (gather them, then wva_pairs_commit)");
         // carve greedy buffers
+        if (T > 256) return fail(ctx, WVA_EINVAL, "the device greedy solver holds at most 256 accelerator types");
+        if ((unsigned long long)(S ? S : 1) * (unsigned long long)A >= (1ull << 31))
+            return fail(ctx, WVA_EINVAL, "servers x accelerators must stay below 2^31 for the greedy solver");
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
         const size_t nS = (size_t)(S ? S : 1);
-        size_t o_order = take(nS * A * 4), o_n = take(nS * 4), o_ci = take(nS * 4), o_d = take(nS * 4), o_st = take(nS * 4),
-               o_heap = take(nS * 4), o_gs = take(104 * 4), o_gi = take(nS * 4), o_un = take(nS * 4), o_ta = take(nS * 4),
-               o_tr = take(nS * 4), o_ts = take(nS), o_av = take((size_t)T * 8), o_nan = take(4), o_key = take(nS * 4);
+        const size_t nSA = nS * A;
+        size_t o_order = take(nSA * 4), o_cand = take(nSA * sizeof(GreedyCand)), o_upr = take(nSA * 8), o_rep = take(nSA * 8), o_ct = take(nSA * 4),
+               o_n = take(nS * 4), o_gs = take(104 * 4), o_gi = take(nS * 4), o_un = take(nS * 4), o_ha = take(nS * 8),
+               o_hb = take(nS * 8), o_hs = take(nS * 4), o_tk = take(nS * sizeof(GreedyTicket)), o_li = take(nS * 4),
+               o_nan = take(8), o_stats = take(32), o_key = take(nS * 4);
+        // ranked queue: states sorted by their fixed key (see k_greedy_solve_ranked)
+        size_t n2 = GREEDY_TILE;
+        while (n2 < nSA) n2 <<= 1;
+        const bool rankable = nSA < (1u << 24) && greedy_bitmap_bytes(nSA, nullptr, nullptr, nullptr) + 4096 <= (size_t)kGreedySmem &&
+                              ctx->greedy_ranked;
+        size_t o_ka = 0, o_kb = 0, o_ks = 0, o_pos = 0, o_sn = 0, o_rec = 0, o_np = 0, o_ge = 0, o_gb = 0, o_top = 0, o_succ = 0;
+        if (rankable) {
+            o_ka = take(n2 * 8); o_kb = take(n2 * 4); o_ks = take(n2 * 4); o_pos = take(nSA * 4); o_sn = take(nSA * 4);
+            o_rec = take(n2 * 16); o_np = take(n2 * 8); o_ge = take(n2 * 4); o_gb = take(n2 * 4); o_top = take((n2 + 1) * 4); o_succ = take(nS * 4);
+        }
         CK(ctx->greedyBuf.ensure(off));
         char* b = ctx->greedyBuf.as<char>();
         GreedyBufs g;
-        g.order = (int*)(b + o_order); g.nCand = (int*)(b + o_n); g.curIndex = (int*)(b + o_ci); g.delta = (float*)(b + o_d);
-        g.stamp = (int*)(b + o_st); g.heap = (int*)(b + o_heap); g.groupStart = (int*)(b + o_gs); g.groupItems = (int*)(b + o_gi);
-        g.unalloc = (int*)(b + o_un); g.ticketAcc = (int*)(b + o_ta); g.ticketRep = (int*)(b + o_tr);
-        g.ticketState = (unsigned char*)(b + o_ts); g.available = (long long*)(b + o_av); g.nanFlag = (int*)(b + o_nan);
+        g.order = (int*)(b + o_order); g.cand = (GreedyCand*)(b + o_cand); g.upr = (long long*)(b + o_upr); g.rep = (long long*)(b + o_rep);
+        g.ctype = (int*)(b + o_ct); g.nCand = (int*)(b + o_n); g.groupStart = (int*)(b + o_gs); g.groupItems = (int*)(b + o_gi);
+        g.unalloc = (int*)(b + o_un); g.heapA = (unsigned long long*)(b + o_ha); g.heapB = (unsigned long long*)(b + o_hb);
+        g.heapSlot = (unsigned*)(b + o_hs); g.tickets = (GreedyTicket*)(b + o_tk); g.liveIdx = (int*)(b + o_li);
+        g.nanFlag = (int*)(b + o_nan);
+        g.stats = (unsigned long long*)(b + o_stats);
+        g.smemBytes = kGreedySmem;
+        GreedyRank gr{};
+        if (rankable) {
+            gr.ka = (unsigned long long*)(b + o_ka); gr.kb = (unsigned*)(b + o_kb); gr.kslot = (unsigned*)(b + o_ks);
+            gr.posOf = (unsigned*)(b + o_pos); gr.snext = (int*)(b + o_sn); gr.rec = (int4*)(b + o_rec); gr.nextPos = (int2*)(b + o_np);
+            gr.gend = (int*)(b + o_ge); gr.gbeg = (int*)(b + o_gb); gr.top = (int*)(b + o_top); gr.succ = (int*)(b + o_succ); gr.n2 = (unsigned)n2;
+        }
+        if (!ctx->greedy_attr) {
+            CK(cudaFuncSetAttribute(k_greedy_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmem));
+            CK(cudaFuncSetAttribute(k_greedy_solve_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmem));
+            ctx->greedy_attr = true;
+        }
         int* chosenKey = (int*)(b + o_key);
         CK(cudaMemsetAsync(g.groupStart, 0, 104 * 4, ctx->stream));
-        CK(cudaMemsetAsync(g.nanFlag, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(g.nanFlag, 0, 8, ctx->stream));
+        CK(cudaMemsetAsync(g.stats, 0, 32, ctx->stream));
         CK(cudaMemsetAsync(chosenKey, 0xff, nS * 4, ctx->stream));
         if (S > 0) {
             k_greedy_prepare<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, ctx->feasible, g);
             LAUNCH_CHECK();
             k_greedy_bucket_count<<<(S + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, g);
             LAUNCH_CHECK();
-            int nanFlag = 0;
-            CK(cudaMemcpyAsync(&nanFlag, g.nanFlag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (rankable) {
+                const unsigned nb = (unsigned)((n2 + 255) / 256), nt = (unsigned)(n2 / GREEDY_TILE);
+                k_greedy_states<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                LAUNCH_CHECK();
+                k_greedy_bitonic_tile<<<nt, 512, 0, ctx->stream>>>(gr, 2u, (unsigned)GREEDY_TILE);
+                LAUNCH_CHECK();
+                for (size_t k = 2 * (size_t)GREEDY_TILE; k <= n2; k <<= 1) {
+                    for (size_t j = k >> 1; j >= (size_t)GREEDY_TILE; j >>= 1) {
+                        k_greedy_bitonic_step<<<(unsigned)((n2 / 2 + 255) / 256), 256, 0, ctx->stream>>>(gr, (unsigned)k, (unsigned)j);
+                        LAUNCH_CHECK();
+                    }
+                    k_greedy_bitonic_tile<<<nt, 512, 0, ctx->stream>>>(gr, (unsigned)k, (unsigned)k);
+                    LAUNCH_CHECK();
+                }
+                CK(cudaMemsetAsync(gr.gend, 0, n2 * 4, ctx->stream));
+                CK(cudaMemsetAsync(gr.top, 0, (n2 + 1) * 4, ctx->stream));
+                k_greedy_index<<<nb, 256, 0, ctx->stream>>>(gr);
+                LAUNCH_CHECK();
+                k_greedy_tie_groups<<<nb, 256, 0, ctx->stream>>>(gr);
+                LAUNCH_CHECK();
+                k_greedy_records<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                LAUNCH_CHECK();
+                k_greedy_tie_init<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                LAUNCH_CHECK();
+            }
+            int flags[2] = {0, 0};                                   // NaN seen, (unused)
+            CK(cudaMemcpyAsync(flags, g.nanFlag, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            if (nanFlag) return fail(ctx, WVA_ENONFINITE, "a candidate value is NaN: the greedy order is undefined");
-            k_greedy_solve<<<1, 32, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, g, chosenKey, spec->delayed_best_effort ? 1 : 0,
-                                                     spec->saturation_policy);
+            if (flags[0]) return fail(ctx, WVA_ENONFINITE, "a candidate value (or the difference of two) is NaN: the greedy order is undefined");
+            ctx->greedy_path = rankable ? 2 : 1;
+            if (ctx->greedy_path == 2) {
+                // shared memory: the rank bitmap, plus the ticket pool when a round-robin policy can
+                // use it; whatever is not asked for stays L1 for the record loads
+                size_t smem = align_up(greedy_bitmap_bytes(nSA, nullptr, nullptr, nullptr), 16);
+                const bool tickets = spec->saturation_policy == WVA_POLICY_ROUND_ROBIN || spec->saturation_policy == WVA_POLICY_PRIORITY_ROUND_ROBIN;
+                if (tickets) smem = std::min((size_t)kGreedySmem, smem + nS * (sizeof(GreedyTicket) + 4));
+                g.smemBytes = (int)smem;
+                k_greedy_solve_ranked<<<1, 32, smem, ctx->stream>>>(ctx->dsys, ctx->pairs, g, gr, chosenKey,
+                                                                   spec->delayed_best_effort ? 1 : 0, spec->saturation_policy);
+            }
+            else
+                k_greedy_solve<<<1, 32, kGreedySmem, ctx->stream>>>(ctx->dsys, ctx->pairs, g, chosenKey, spec->delayed_best_effort ? 1 : 0,
+                                                                   spec->saturation_policy);
             LAUNCH_CHECK();
-            k_greedy_collect<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, chosenKey, ctx->chosen_acc, ctx->chosen);
+            ctx->greedy_stats_dev = g.stats;
+            k_greedy_collect<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->dsys, ctx->pairs, g.order, chosenKey, ctx->chosen_acc, ctx->chosen);
             LAUNCH_CHECK();
         }
         // best-effort scaling mutated the candidate records in place (greedy.go:208-212): the
@@ -825,11 +902,25 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
     CK(cudaStreamSynchronize(ctx->stream));
     timer.stop();
     ctx->solved = true;
+    if (!spec->unlimited && S > 0 && ctx->greedy_stats_dev)
+        CK(cudaMemcpy(ctx->greedy_stats, ctx->greedy_stats_dev, 32, cudaMemcpyDeviceToHost));
     if (count > 0) {
         if (chosen_acc) CK(cudaMemcpyAsync(chosen_acc + first, ctx->chosen_acc + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (chosen) CK(download_allocs(ctx, ctx->chosen, (size_t)first, (size_t)count, chosen, (size_t)first));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return WVA_OK;
+}
+
+int wva_solve_set_ranked(wva_ctx* ctx, int32_t on) {
+    if (!ctx) return WVA_EINVAL;
+    ctx->greedy_ranked = on ? 1 : 0;
+    return WVA_OK;
+}
+int wva_solve_greedy_path(const wva_ctx* ctx) { return ctx ? ctx->greedy_path : WVA_EINVAL; }
+int wva_solve_stats(wva_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return WVA_EINVAL;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->greedy_stats[i];
     return WVA_OK;
 }
 
@@ -842,7 +933,7 @@ int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost) {
     PhaseTimer timer(ctx, WVA_PHASE_TOTALS);
     long long* dcount = ctx->totals.as<long long>();
     float* dcost = (float*)(ctx->totals.as<char>() + (size_t)T * 8);
-    k_totals<<<(T + 31) / 32, 32, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->ns, ctx->chosen_acc, ctx->chosen, dcount, dcost);
+    k_totals<<<T, 1024, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->ns, ctx->chosen_acc, ctx->chosen, dcount, dcost);
     LAUNCH_CHECK();
     timer.stop();
     if (count) CK(cudaMemcpyAsync(count, dcount, (size_t)T * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -856,6 +947,17 @@ int wva_type_totals_device(wva_ctx* ctx, void** dev_ptr, size_t* bytes) {
     if (!ctx->totals.p) return fail(ctx, WVA_ESTATE, "wva_allocate_by_type has not run");
     *dev_ptr = ctx->totals.p;
     if (bytes) *bytes = (size_t)ctx->T * 12;
+    return WVA_OK;
+}
+
+int wva_type_totals_merge(wva_ctx* ctx, const void* gathered_dev, int32_t n_ranks) {
+    if (!ctx || !gathered_dev || n_ranks < 1) return fail(ctx, WVA_EINVAL, "null argument");
+    if (!ctx->totals.p) return fail(ctx, WVA_ESTATE, "wva_allocate_by_type has not run");
+    CK(cudaSetDevice(ctx->device));
+    const int T = ctx->T;
+    k_totals_merge<<<(T + 63) / 64, 64, 0, ctx->stream>>>(T, n_ranks, (const unsigned char*)gathered_dev, ctx->totals.as<long long>(),
+                                                         (float*)(ctx->totals.as<char>() + (size_t)T * 8));
+    LAUNCH_CHECK();
     return WVA_OK;
 }
 

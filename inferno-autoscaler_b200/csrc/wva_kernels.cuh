@@ -1322,22 +1322,63 @@ __global__ void k_solve_unlimited(DevSystem sys, int s0, int ns, DevAllocs pairs
     store_alloc(chosen, (size_t)s, minKey >= 0 ? load_alloc(pairs, (size_t)s * sys.A + minKey) : empty_alloc());
 }
 
-// System.AllocateByType (system.go:271-300) over servers [s0, s0+ns): one thread per accelerator
-// type walks the servers in ascending index, so the float32 cost sum has a fixed order.
+// System.AllocateByType (system.go:271-300) over servers [s0, s0+ns): one block per accelerator
+// type.  The float32 cost sum keeps a fixed order (ascending server index): the block stages 1024
+// servers' contributions in shared memory in parallel, then warp 0 adds them in order (a server
+// of another type contributes +0, which leaves a float32 sum that started at +0 unchanged).
+// The int64 unit counts wrap and are associative: plain tree reduction.
 // totals = { long long count[T]; float cost[T] }.
-__global__ void k_totals(DevSystem sys, int s0, int ns, const int* __restrict__ chosen_acc, DevAllocs chosen,
-                         long long* __restrict__ count, float* __restrict__ cost) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= sys.T) return;
+__global__ void __launch_bounds__(1024) k_totals(DevSystem sys, int s0, int ns, const int* __restrict__ chosen_acc, DevAllocs chosen,
+                                                 long long* __restrict__ count, float* __restrict__ cost) {
+    __shared__ float vals[1024];
+    __shared__ long long part[32];
+    const int t = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long c = 0; float k = 0.0f;
-    for (int s = s0; s < s0 + ns; ++s) {
-        if (chosen_acc[s] < 0) continue;
-        int gi = chosen.acc[s];
-        int m = sys.srv_model[s];
-        if (gi < 0 || m < 0) continue;
-        if (sys.acc_type[gi] != t) continue;
-        c += go_muli(go_muli(chosen.num_replicas[s], num_instances(sys, m, gi)), (long long)sys.acc_multiplicity[gi]);
-        k = k + chosen.cost[s];
+    for (int base = 0; base < ns; base += 1024) {
+        const int s = s0 + base + tid;
+        float v = 0.0f;
+        if (base + tid < ns && chosen_acc[s] >= 0) {
+            const int gi = chosen.acc[s];
+            const int m = sys.srv_model[s];
+            if (gi >= 0 && m >= 0 && sys.acc_type[gi] == t) {
+                c += go_muli(go_muli(chosen.num_replicas[s], num_instances(sys, m, gi)), (long long)sys.acc_multiplicity[gi]);
+                v = chosen.cost[s];
+            }
+        }
+        vals[tid] = v;
+        __syncthreads();
+        if (warp == 0) {
+            const int cnt = min(1024, ns - base);
+            for (int b = 0; b < cnt; b += 32) {
+                const float mine = vals[b + lane];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) k = k + __shfl_sync(0xffffffffu, mine, j);
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (lane == 0) part[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+        long long tot = 0;
+        for (int w = 0; w < 32; ++w) tot += part[w];
+        count[t] = tot; cost[t] = k;
+    }
+}
+
+// Sum the per-rank partial totals of a sharded run in rank order (deterministic, unlike a ring or
+// tree all-reduce): gathered = n_ranks blocks of { long long count[T]; float cost[T] }.
+__global__ void k_totals_merge(int T, int n_ranks, const unsigned char* __restrict__ gathered, long long* __restrict__ count,
+                               float* __restrict__ cost) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    long long c = 0; float k = 0.0f;
+    for (int r = 0; r < n_ranks; ++r) {
+        const unsigned char* blk = gathered + (size_t)r * T * 12;
+        c += reinterpret_cast<const long long*>(blk)[t];
+        k = k + reinterpret_cast<const float*>(blk + (size_t)T * 8)[t];
     }
     count[t] = c; cost[t] = k;
 }
@@ -1354,160 +1395,250 @@ __device__ __forceinline__ int go_cmpf(float x, float y) {
     return 0;
 }
 
+struct GreedyTicket {      // allocateEqually's serverAllocationTicket (greedy.go:226-236)
+    long long upr;         // units one replica takes
+    long long cur;         // replicas the candidate wants
+    long long got;         // replicas handed out
+    int slot;              // s*A + position in the server's candidate order (-1: none)
+    int type;
+};
+
+// what the sequential pass reads of one candidate: one 16-byte load; a server's candidates are
+// contiguous (one 128-byte line for 8 accelerators)
+struct __align__(16) GreedyCand {
+    long long count;       // units the candidate takes: replicas x instances x multiplicity
+    float val;
+    int tf;                // type | GREEDY_LAST (server's last candidate) | GREEDY_SKIP (no accelerator)
+};
+constexpr int GREEDY_LAST = 1 << 16, GREEDY_SKIP = 1 << 17;
+
 struct GreedyBufs {
-    int* order;            // [S*A] per server: candidate keys sorted by value (stable on accelerator index)
+    // per server, candidates in greedy order (ascending value, stable on accelerator index)
+    int* order;            // [S*A] candidate key (accelerator index)
+    GreedyCand* cand;      // [S*A]
+    long long* upr;        // [S*A] units per replica (instances x multiplicity)
+    long long* rep;        // [S*A] replicas
+    int* ctype;            // [S*A] accelerator type, -1 when the candidate has no accelerator
     int* nCand;            // [S]
-    int* curIndex;         // [S]
-    float* delta;          // [S]
-    int* stamp;            // [S] recency stamp (initial -server index)
-    int* heap;             // [S] server ids
     int* groupStart;       // [102] population / start offset of each priority (1..100)
     int* groupItems;       // [S]
     int* unalloc;          // [S]
-    int* ticketAcc;        // [S] allocateEqually: chosen candidate key
-    int* ticketRep;        // [S] replicas handed out
-    unsigned char* ticketState;   // [S] 0 absent, 1 present, 2 active
-    long long* available;  // [T]
-    int* nanFlag;          // [1]
+    unsigned long long* heapA;   // [S] heap storage used when a group does not fit shared memory
+    unsigned long long* heapB;   // [S]
+    unsigned* heapSlot;          // [S]
+    GreedyTicket* tickets;       // [S] ditto for allocateEqually
+    int* liveIdx;                // [S]
+    int* nanFlag;          // [2]
+    unsigned long long* stats;   // [4] instrumentation: queue pops, failed placements, cycles in the queue loop, cycles in bestEffort
+    int smemBytes;         // dynamic shared memory handed to k_greedy_solve
 };
 
-// per server: sort candidate keys by value (greedy.go:57-63), initial delta (:64-71)
+// per server: sort candidate keys by value (greedy.go:57-63) and lay the fields the sequential
+// pass reads out in that order, so that one pop costs one dependent load
 __global__ void k_greedy_prepare(DevSystem sys, DevAllocs pairs, const unsigned char* __restrict__ feasible, GreedyBufs g) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sys.S) return;
-    int* ord = g.order + (size_t)s * sys.A;
+    const size_t base = (size_t)s * sys.A;
+    int* ord = g.order + base;
     int n = 0;
     for (int a = 0; a < sys.A; ++a) {
-        size_t i = (size_t)s * sys.A + a;
+        size_t i = base + a;
         if (!feasible[i]) continue;
         float v = pairs.value[i];
         if (v != v) atomicExch(g.nanFlag, 1);
         int j = n++;
         // stable insertion sort by cmp.Compare(value)
-        while (j > 0 && go_cmpf(pairs.value[(size_t)s * sys.A + ord[j - 1]], v) > 0) { ord[j] = ord[j - 1]; --j; }
+        while (j > 0 && go_cmpf(pairs.value[base + ord[j - 1]], v) > 0) { ord[j] = ord[j - 1]; --j; }
         ord[j] = a;
     }
     g.nCand[s] = n;
-    g.curIndex[s] = 0;
-    g.stamp[s] = -s;
-    float d = 0.0f;
-    if (n > 1) d = pairs.value[(size_t)s * sys.A + ord[1]] - pairs.value[(size_t)s * sys.A + ord[0]];
-    else if (n == 1) d = 3.40282346638528859811704183484516925e+38f;
-    g.delta[s] = d;
+    const int m = sys.srv_model[s];
+    float prev = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        size_t ai = base + ord[k];
+        float v = pairs.value[ai];
+        // the deltas of greedy.go:64-71/:147-153 are differences of neighbours in this order; an
+        // inf-inf makes the order of the reference depend on evaluation order: refuse
+        if (k > 0) { float d = v - prev; if (d != d) atomicExch(g.nanFlag, 1); }
+        prev = v;
+        int gi = pairs.acc[ai];
+        long long upr = 0; int t = -1;
+        if (m >= 0 && gi >= 0) { upr = go_muli(num_instances(sys, m, gi), (long long)sys.acc_multiplicity[gi]); t = sys.acc_type[gi]; }
+        const long long reps = pairs.num_replicas[ai];
+        g.upr[base + k] = upr;
+        g.rep[base + k] = reps;
+        g.ctype[base + k] = t;
+        GreedyCand cd;
+        cd.count = go_muli(reps, upr);
+        cd.val = v;
+        cd.tf = (t < 0 ? GREEDY_SKIP : t) | (k == n - 1 ? GREEDY_LAST : 0);
+        g.cand[base + k] = cd;
+    }
+}
+
+// monotone map float32 -> uint32 for cmp.Compare on non-NaN values (-0 and +0 coincide)
+__device__ __forceinline__ unsigned f32_sortable(float f) {
+    f = f + 0.0f;
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// orderFunc, greedy.go:76-85, as a pair of ascending 64-bit keys: priority ascending, delta
+// descending, current value descending, and -- refining ties into a strict order -- the recency
+// stamp descending: an entry re-inserted by slices.BinarySearchFunc lands before every equal
+// entry (largest stamp first); the initial stable sort keeps equal entries in ascending server
+// index (stamp = -index).
+__device__ __forceinline__ void greedy_keys(int priority, float delta, float value, int stamp,
+                                            unsigned long long& ka, unsigned long long& kb) {
+    ka = ((unsigned long long)(unsigned)priority << 32) | (unsigned)~f32_sortable(delta);
+    kb = ((unsigned long long)(unsigned)~f32_sortable(value) << 32) | (unsigned)~((unsigned)stamp + 0x80000000u);
+}
+
+// 4-ary min-heap on (a, b), structure of arrays so that shared memory is used to the byte
+struct GreedyHeap {
+    unsigned long long* a; unsigned long long* b; unsigned* slot; int n;
+    // place (va,vb,vs) at or below position i
+    __device__ __forceinline__ void siftDown(int i, unsigned long long va, unsigned long long vb, unsigned vs) {
+        for (;;) {
+            const int l = 4 * i + 1;
+            if (l >= n) break;
+            int c = l;
+            unsigned long long ca = a[l], cb = b[l];
+            if (l + 3 < n) {
+                const unsigned long long a1 = a[l + 1], b1 = b[l + 1], a2 = a[l + 2], b2 = b[l + 2], a3 = a[l + 3], b3 = b[l + 3];
+                if (a1 < ca || (a1 == ca && b1 < cb)) { c = l + 1; ca = a1; cb = b1; }
+                if (a2 < ca || (a2 == ca && b2 < cb)) { c = l + 2; ca = a2; cb = b2; }
+                if (a3 < ca || (a3 == ca && b3 < cb)) { c = l + 3; ca = a3; cb = b3; }
+            } else {
+                for (int k = l + 1; k < n; ++k) {
+                    const unsigned long long ak = a[k], bk = b[k];
+                    if (ak < ca || (ak == ca && bk < cb)) { c = k; ca = ak; cb = bk; }
+                }
+            }
+            if (!(ca < va || (ca == va && cb < vb))) break;
+            a[i] = ca; b[i] = cb; slot[i] = slot[c];
+            i = c;
+        }
+        a[i] = va; b[i] = vb; slot[i] = vs;
+    }
+    __device__ __forceinline__ void popRoot() {
+        --n;
+        if (n > 0) siftDown(0, a[n], b[n], slot[n]);
+    }
+};
+
+// pull a candidate record's line into L1 ahead of its use (no destination register: never waited on)
+__device__ __forceinline__ void greedy_touch(const GreedyCand* p) {
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
 struct GreedyCtx {
     DevSystem sys; DevAllocs pairs; GreedyBufs g; int* chosen;
-    __device__ __forceinline__ float curValue(int s) const {
-        return pairs.value[(size_t)s * sys.A + g.order[(size_t)s * sys.A + g.curIndex[s]]];
-    }
-    // orderFunc, greedy.go:76-85, refined to a strict order by the recency stamp: an entry
-    // re-inserted by slices.BinarySearchFunc lands before every equal entry (largest stamp first);
-    // the initial stable sort keeps equal entries in ascending server index (stamp = -index).
-    __device__ __forceinline__ bool before(int x, int y) const {
-        int px = sys.srv_priority[x], py = sys.srv_priority[y];
-        if (px != py) return px < py;
-        float dx = g.delta[x], dy = g.delta[y];
-        int c;
-        if (dx == dy) c = go_cmpf(curValue(y), curValue(x));
-        else c = go_cmpf(dy, dx);
-        if (c != 0) return c < 0;
-        return g.stamp[x] > g.stamp[y];
-    }
-    __device__ void siftDown(int* h, int n, int i) const {
-        int v = h[i];
-        for (;;) {
-            int l = 2 * i + 1;
-            if (l >= n) break;
-            int r = l + 1;
-            int c = (r < n && before(h[r], h[l])) ? r : l;
-            if (!before(h[c], v)) break;
-            h[i] = h[c]; i = c;
-        }
-        h[i] = v;
-    }
-    __device__ void siftUp(int* h, int i) const {
-        int v = h[i];
-        while (i > 0) {
-            int p = (i - 1) >> 1;
-            if (!before(v, h[p])) break;
-            h[i] = h[p]; i = p;
-        }
-        h[i] = v;
-    }
-    __device__ __forceinline__ long long unitsPerReplica(int s, int gi) const {
-        return go_muli(num_instances(sys, sys.srv_model[s], gi), (long long)sys.acc_multiplicity[gi]);
-    }
-    __device__ __forceinline__ int candKey(int s, int idx) const { return g.order[(size_t)s * sys.A + idx]; }
+    long long* avail;          // [T] shared memory
+    long long* usum;           // [T] shared memory scratch (allocateEqually)
+    unsigned char* pool;       // dynamic shared memory
+    int lane;
 };
 
-// allocate, greedy.go:107-166, over the servers in items[0..n); returns number of unallocated
-// entries appended to g.unalloc (starting at unallocBase).
-__device__ int greedy_allocate(GreedyCtx& c, const int* items, int n, int unallocBase) {
-    int* h = c.g.heap;
+// allocate, greedy.go:107-166, over the servers in items[0..n); returns the number of unallocated
+// entries written to g.unalloc.  The warp builds the queue; lane 0 runs the sequential pass.
+__device__ int greedy_allocate(GreedyCtx& c, const int* items, int n) {
+    const int A = c.sys.A;
+    GreedyHeap h;
+    if ((size_t)n * 20 <= (size_t)c.g.smemBytes) {
+        h.a = reinterpret_cast<unsigned long long*>(c.pool);
+        h.b = h.a + n;
+        h.slot = reinterpret_cast<unsigned*>(h.b + n);
+    } else { h.a = c.g.heapA; h.b = c.g.heapB; h.slot = c.g.heapSlot; }
     int hn = 0;
-    for (int i = 0; i < n; ++i) if (c.g.nCand[items[i]] > 0) h[hn++] = items[i];
-    for (int i = hn / 2 - 1; i >= 0; --i) c.siftDown(h, hn, i);
-    int stampCounter = 1;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + c.lane;
+        int s = i < n ? items[i] : -1;
+        int nc = s >= 0 ? c.g.nCand[s] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, nc > 0);
+        if (nc > 0) {
+            size_t base = (size_t)s * A;
+            float v0 = c.g.cand[base].val;
+            float d = nc > 1 ? c.g.cand[base + 1].val - v0 : 3.40282346638528859811704183484516925e+38f;
+            int pos = hn + __popc(m & ((1u << c.lane) - 1u));
+            greedy_keys(c.sys.srv_priority[s], d, v0, -s, h.a[pos], h.b[pos]);
+            h.slot[pos] = (unsigned)base;
+        }
+        hn += __popc(m);
+    }
+    __syncwarp();
     int nUn = 0;
-    while (hn > 0) {
-        int s = h[0];
-        h[0] = h[--hn];
-        if (hn > 0) c.siftDown(h, hn, 0);
-        if (c.sys.srv_model[s] < 0) continue;
-        int key = c.candKey(s, c.g.curIndex[s]);
-        size_t ai = (size_t)s * c.sys.A + key;
-        int gi = c.pairs.acc[ai];
-        if (gi < 0) continue;                                       // GetAccelerator("") == nil
-        int t = c.sys.acc_type[gi];
-        long long count = go_muli(c.pairs.num_replicas[ai], c.unitsPerReplica(s, gi));
-        if (c.g.available[t] >= count) {
-            c.g.available[t] -= count;
-            c.chosen[s] = key;
-        } else {
-            int ci = ++c.g.curIndex[s];
-            int len = c.g.nCand[s];
-            if (ci + 1 < len) {
-                c.g.delta[s] = c.pairs.value[(size_t)s * c.sys.A + c.candKey(s, ci + 1)] -
-                               c.pairs.value[(size_t)s * c.sys.A + c.candKey(s, ci)];
-            } else if (ci == len) {
-                c.g.unalloc[unallocBase + nUn++] = s;
-                continue;
-            } else {
-                c.g.delta[s] = 3.40282346638528859811704183484516925e+38f;
+    if (c.lane == 0) {
+        h.n = hn;
+        for (int i = (hn - 2) / 4; i >= 0 && hn > 1; --i) h.siftDown(i, h.a[i], h.b[i], h.slot[i]);
+        int stampCounter = 1;
+        while (h.n > 0) {
+            const unsigned slot = h.slot[0];
+            const int4 raw = *reinterpret_cast<const int4*>(c.g.cand + slot);
+            // the next roots come from the top two levels: start their loads now
+            {
+                const int lim = h.n < 21 ? h.n : 21;
+                for (int q = 1; q < lim; ++q) greedy_touch(c.g.cand + h.slot[q]);
             }
-            c.g.stamp[s] = stampCounter++;
-            h[hn] = s;
-            c.siftUp(h, hn);
-            ++hn;
+            const int tf = raw.w;
+            const int s = (int)(slot / (unsigned)A);
+            if (tf & GREEDY_SKIP) { h.popRoot(); continue; }             // no model / GetAccelerator("") == nil
+            const int t = tf & 0xffff;
+            const long long count = (long long)(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x);
+            if (c.avail[t] >= count) {
+                c.avail[t] -= count;
+                c.chosen[s] = (int)slot;
+                h.popRoot();
+                continue;
+            }
+            if (tf & GREEDY_LAST) { c.g.unalloc[nUn++] = s; h.popRoot(); continue; }
+            const GreedyCand nx = c.g.cand[slot + 1];
+            const float d = (nx.tf & GREEDY_LAST) ? 3.40282346638528859811704183484516925e+38f : c.g.cand[slot + 2].val - nx.val;
+            unsigned long long ka, kb;
+            greedy_keys((int)(h.a[0] >> 32), d, nx.val, stampCounter++, ka, kb);
+            h.siftDown(0, ka, kb, slot + 1);
         }
     }
+    nUn = __shfl_sync(0xffffffffu, nUn, 0);
+    __syncwarp();
     return nUn;
 }
 
-// allocateMaximally, greedy.go:194-223
+// scale the chosen candidate to `got` of its `cur` replicas (greedy.go:208-212, :305-311)
+__device__ __forceinline__ void greedy_scale(GreedyCtx& c, int s, int slot, long long got, long long cur) {
+    const int key = c.g.order[slot];
+    const size_t ai = (size_t)s * c.sys.A + key;
+    const float factor = (float)got / (float)cur;
+    c.pairs.cost[ai] = c.pairs.cost[ai] * factor;
+    c.pairs.value[ai] = c.pairs.value[ai] * factor;
+    c.pairs.num_replicas[ai] = got;
+    c.chosen[s] = slot;
+}
+
+// allocateMaximally, greedy.go:194-223: lane k looks at candidate k, the first lane that can
+// place at least one replica takes it
 __device__ void greedy_allocate_maximally(GreedyCtx& c, const int* list, int n) {
+    const int A = c.sys.A;
     for (int i = 0; i < n; ++i) {
-        int s = list[i];
+        const int s = list[i];
         if (c.sys.srv_model[s] < 0) continue;
-        for (int k = 0; k < c.g.nCand[s]; ++k) {
-            int key = c.candKey(s, k);
-            size_t ai = (size_t)s * c.sys.A + key;
-            int gi = c.pairs.acc[ai];
-            if (gi < 0) continue;
-            long long upr = c.unitsPerReplica(s, gi);
-            if (upr <= 0) continue;
-            int t = c.sys.acc_type[gi];
-            long long cur = c.pairs.num_replicas[ai];
-            long long maxRep = go_divi(c.g.available[t], upr);
-            if (cur < maxRep) maxRep = cur;
-            if (maxRep > 0) {
-                float factor = (float)maxRep / (float)cur;
-                c.pairs.cost[ai] = c.pairs.cost[ai] * factor;
-                c.pairs.value[ai] = c.pairs.value[ai] * factor;
-                c.pairs.num_replicas[ai] = maxRep;
-                c.chosen[s] = key;
-                c.g.available[t] -= go_muli(maxRep, upr);
+        const int nc = c.g.nCand[s];
+        for (int k0 = 0; k0 < nc; k0 += 32) {
+            const int k = k0 + c.lane;
+            long long maxRep = 0, upr = 0, cur = 0; int t = -1;
+            const int slot = s * A + k;
+            if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; cur = c.g.rep[slot]; }
+            if (t >= 0 && upr > 0) {
+                maxRep = go_divi(c.avail[t], upr);
+                if (cur < maxRep) maxRep = cur;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, maxRep > 0);
+            if (m) {
+                if (c.lane == __ffs(m) - 1) {
+                    greedy_scale(c, s, slot, maxRep, cur);
+                    c.avail[t] -= go_muli(maxRep, upr);
+                }
+                __syncwarp();
                 break;
             }
         }
@@ -1516,59 +1647,84 @@ __device__ void greedy_allocate_maximally(GreedyCtx& c, const int* list, int n) 
 
 // allocateEqually, greedy.go:239-316
 __device__ void greedy_allocate_equally(GreedyCtx& c, const int* list, int n) {
+    const int A = c.sys.A;
+    GreedyTicket* tk; int* liveIdx;
+    if ((size_t)n * (sizeof(GreedyTicket) + 4) <= (size_t)c.g.smemBytes) {
+        tk = reinterpret_cast<GreedyTicket*>(c.pool);
+        liveIdx = reinterpret_cast<int*>(tk + n);
+    } else { tk = c.g.tickets; liveIdx = c.g.liveIdx; }
+    // round 1: every present ticket picks the first candidate with room for one replica
+    // (lane k looks at candidate k), then takes its first replica
     int live = 0;
     for (int i = 0; i < n; ++i) {
-        int s = list[i];
-        c.g.ticketRep[s] = 0; c.g.ticketAcc[s] = -1;
-        if (c.sys.srv_model[s] < 0) { c.g.ticketState[s] = 0; continue; }
-        c.g.ticketState[s] = 1; ++live;
-    }
-    while (live > 0) {
-        for (int i = 0; i < n; ++i) {
-            int s = list[i];
-            unsigned char stt = c.g.ticketState[s];
-            if (stt == 0) continue;
-            if (stt == 1) {
-                bool found = false;
-                for (int k = 0; k < c.g.nCand[s]; ++k) {
-                    int key = c.candKey(s, k);
-                    int gi = c.pairs.acc[(size_t)s * c.sys.A + key];
-                    if (gi < 0) continue;
-                    long long upr = c.unitsPerReplica(s, gi);
-                    if (upr > 0 && c.g.available[c.sys.acc_type[gi]] >= upr) { c.g.ticketAcc[s] = key; found = true; break; }
+        const int s = list[i];
+        GreedyTicket me; me.upr = 0; me.cur = 0; me.slot = -1; me.got = 0; me.type = -1;
+        int state = 0;                                               // 0 absent, 2 active
+        if (c.sys.srv_model[s] >= 0) {
+            const int nc = c.g.nCand[s];
+            for (int k0 = 0; k0 < nc && state == 0; k0 += 32) {
+                const int k = k0 + c.lane;
+                long long upr = 0; int t = -1;
+                const int slot = s * A + k;
+                if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; }
+                const bool fits = t >= 0 && upr > 0 && c.avail[t] >= upr;
+                const unsigned m = __ballot_sync(0xffffffffu, fits);
+                if (m) {
+                    const int src = __ffs(m) - 1;
+                    me.slot = __shfl_sync(0xffffffffu, slot, src);
+                    me.upr = __shfl_sync(0xffffffffu, upr, src);
+                    me.type = __shfl_sync(0xffffffffu, t, src);
+                    me.cur = c.g.rep[me.slot];
+                    state = 2;
                 }
-                if (!found) { c.g.ticketState[s] = 0; --live; continue; }
-                c.g.ticketState[s] = 2;
             }
-            int key = c.g.ticketAcc[s];
-            size_t ai = (size_t)s * c.sys.A + key;
-            int gi = c.pairs.acc[ai];
-            int t = c.sys.acc_type[gi];
-            long long upr = c.unitsPerReplica(s, gi);
-            long long avail = go_divi(c.g.available[t], upr);
-            long long cur = c.pairs.num_replicas[ai];
-            long long allocatable = avail < cur ? avail : cur;
-            if (allocatable > 0) {
-                c.g.ticketRep[s]++;
-                c.g.available[t] -= upr;
-            } else {
-                c.g.ticketState[s] = 0; --live;
+            if (state == 2) {
+                // allocatable = min(available/upr, cur) > 0, with upr > 0
+                if (c.avail[me.type] >= me.upr && me.cur > 0) {
+                    me.got = 1;
+                    __syncwarp();
+                    if (c.lane == 0) { c.avail[me.type] -= me.upr; liveIdx[live] = i; }
+                    ++live;
+                }
+            }
+        }
+        if (c.lane == 0) tk[i] = me;
+        __syncwarp();
+    }
+    // later rounds: one replica per live ticket per round, in list order.  A round in which every
+    // live ticket is served takes sum(upr) per type, so k = min over types of avail / sum such rounds
+    // can be applied at once (same result as running them: nobody drops out before round k+1).
+    if (c.lane == 0) {
+        const int T = c.sys.T;
+        while (live > 0) {
+            int w = 0;
+            for (int j = 0; j < live; ++j) {
+                const int i = liveIdx[j];
+                GreedyTicket& me = tk[i];
+                if (c.avail[me.type] >= me.upr && me.cur > 0) {
+                    me.got++;
+                    c.avail[me.type] -= me.upr;
+                    liveIdx[w++] = i;
+                }
+            }
+            live = w;
+            if (live == 0) break;
+            for (int t = 0; t < T; ++t) c.usum[t] = 0;
+            for (int j = 0; j < live; ++j) { const GreedyTicket& me = tk[liveIdx[j]]; c.usum[me.type] += me.upr; }
+            long long k = 0x7fffffffffffffffLL;
+            for (int t = 0; t < T; ++t) if (c.usum[t] > 0) { const long long kt = c.avail[t] / c.usum[t]; if (kt < k) k = kt; }
+            if (k > 0 && k < 0x7fffffffffffffffLL) {
+                for (int t = 0; t < T; ++t) if (c.usum[t] > 0) c.avail[t] -= k * c.usum[t];
+                for (int j = 0; j < live; ++j) tk[liveIdx[j]].got += k;
             }
         }
     }
-    for (int i = 0; i < n; ++i) {
-        int s = list[i];
-        int got = c.g.ticketRep[s];
-        if (got <= 0) continue;
-        int key = c.g.ticketAcc[s];
-        size_t ai = (size_t)s * c.sys.A + key;
-        long long cur = c.pairs.num_replicas[ai];
-        float factor = (float)got / (float)cur;
-        c.pairs.cost[ai] = c.pairs.cost[ai] * factor;
-        c.pairs.value[ai] = c.pairs.value[ai] * factor;
-        c.pairs.num_replicas[ai] = got;
-        c.chosen[s] = key;
+    __syncwarp();
+    for (int i = c.lane; i < n; i += 32) {
+        const GreedyTicket me = tk[i];
+        if (me.got > 0) greedy_scale(c, list[i], me.slot, me.got, me.cur);
     }
+    __syncwarp();
 }
 
 // bestEffort, greedy.go:169-190 (list is grouped by priority already)
@@ -1595,39 +1751,409 @@ __global__ void k_greedy_bucket_count(DevSystem sys, GreedyBufs g) {
     atomicAdd(&g.groupStart[sys.srv_priority[s]], 1);
 }
 
-// SolveGreedy, greedy.go:35-104: the sequential assignment.  One thread: every step depends on
-// the capacities left by the previous one.  Servers are bucketed by priority; inside a bucket the
-// binary heap reproduces the sorted-slice order of the reference (see GreedyCtx::before).
-__global__ void k_greedy_solve(DevSystem sys, DevAllocs pairs, GreedyBufs g, int* chosen, int delayedBestEffort, int policy) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    GreedyCtx c; c.sys = sys; c.pairs = pairs; c.g = g; c.chosen = chosen;
-    for (int t = 0; t < sys.T; ++t) g.available[t] = sys.type_capacity[t];
+// SolveGreedy, greedy.go:35-104: the sequential assignment, one warp.  Every step depends on the
+// capacities left by the previous one, so lane 0 walks a priority queue held in shared memory
+// (two 64-bit keys + a slot per entry; see greedy_keys); the other lanes help where the reference
+// scans a server's candidates or builds lists.  Servers are bucketed by priority first.
+__global__ void __launch_bounds__(32) k_greedy_solve(DevSystem sys, DevAllocs pairs, GreedyBufs g, int* chosen,
+                                                       int delayedBestEffort, int policy) {
+    extern __shared__ __align__(16) unsigned char greedy_pool[];
+    __shared__ long long avail[256];
+    __shared__ long long usum[256];
+    __shared__ int cursor[104];
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
+    GreedyCtx c; c.sys = sys; c.pairs = pairs; c.g = g; c.chosen = chosen; c.avail = avail; c.usum = usum; c.pool = greedy_pool; c.lane = lane;
+    for (int t = lane; t < sys.T; t += 32) avail[t] = sys.type_capacity[t];
     // groupStart[p] holds the population of priority p (1..100): exclusive prefix sum, then a
     // stable scatter in ascending server index
-    int cursor[102];
-    int run = 0;
-    for (int p = 0; p <= 101; ++p) { int cnt = g.groupStart[p]; g.groupStart[p] = run; cursor[p] = run; run += cnt; }
-    for (int s = 0; s < sys.S; ++s) g.groupItems[cursor[sys.srv_priority[s]]++] = s;
+    if (lane == 0) {
+        int run = 0;
+        for (int p = 0; p <= 101; ++p) { int cnt = g.groupStart[p]; g.groupStart[p] = run; cursor[p] = run; run += cnt; }
+    }
+    __syncwarp();
+    for (int s0 = 0; s0 < sys.S; s0 += 32) {
+        const int s = s0 + lane;
+        const int p = s < sys.S ? sys.srv_priority[s] : 101;
+        const unsigned peers = __match_any_sync(0xffffffffu, p);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (s < sys.S) g.groupItems[cursor[p] + rank] = s;
+        __syncwarp();
+        if (rank == 0) cursor[p] += __popc(peers);
+        __syncwarp();
+    }
+    __threadfence_block();
     if (delayedBestEffort) {
         // one allocate() over everything (the comparator orders by priority first), then one bestEffort
-        int nUn = greedy_allocate(c, g.groupItems, sys.S, 0);
+        int nUn = greedy_allocate(c, g.groupItems, sys.S);
         greedy_best_effort(c, g.unalloc, nUn, policy);
     } else {
         for (int p = 1; p <= 100; ++p) {                              // makePriorityGroups(entries), :96-103
             int lo = g.groupStart[p], hi = g.groupStart[p + 1];
             if (hi <= lo) continue;
-            int nUn = greedy_allocate(c, g.groupItems + lo, hi - lo, 0);
+            int nUn = greedy_allocate(c, g.groupItems + lo, hi - lo);
             greedy_best_effort(c, g.unalloc, nUn, policy);
         }
     }
 }
 
+// ---- greedy, ranked-queue path -----------------------------------------------------------------
+// Every entry the reference's sorted slice can ever hold is one of the S*A states (server, position
+// in its candidate order), and the key of a state -- priority, delta to the next candidate, value
+// -- is fixed once the candidates are sized.  Sorting the states once (bitonic network, all SMs)
+// turns the comparator into an integer rank; the queue becomes a bitmap over ranks in shared
+// memory (64-ary, 4 levels) and a pop is four find-first-set steps plus one 16-byte record load.
+// Only the recency tie-break of greedy_keys is dynamic.  States with one key (a "tie group", e.g.
+// zero-load servers on the same accelerator) sort next to each other; among them the reference
+// pops the most recently inserted first, the initial entries in ascending server index last.
+// That is a stack: a tie group hands its rank range out from the top end downwards, so the entry
+// inserted last always holds the smallest occupied rank of the group, and the record stored at a
+// rank of a tie group is written when the entry is inserted.
+
+struct GreedyRank {
+    unsigned long long* ka;    // [N2] sort key: priority << 32 | ~sortable(delta)
+    unsigned* kb;              // [N2]           ~sortable(value)
+    unsigned* kslot;           // [N2] payload: state s*A+k, 0xffffffff for padding
+    unsigned* posOf;           // [S*A] rank of a state (initial entries of a tie group: the rank handed out)
+    int* snext;                // [S*A] where the server's next state goes: -1 none, >= 0 its rank, <= -2: tie group starting at -2-x
+    int4* rec;                 // [N2] per rank: { count lo, count hi, tf | priority << 18 | GREEDY_TIE, state }
+    int2* nextPos;             // [N2] per rank: { snext of the state stored there, end of the rank's tie group or 0 }
+    int* gend;                 // [N2] per rank: end of its tie group, 0 outside tie groups
+    int* gbeg;                 // [N2] per rank: start of its tie group (valid where gend != 0)
+    int* top;                  // [N2+1] per tie group (indexed by its end): entries currently queued
+    int* succ;                 // [S] log of the states placed by the queue loop
+    unsigned n2;               // padded length (power of two)
+};
+constexpr int GREEDY_TIE = 1 << 25;
+
+constexpr int GREEDY_TILE = 2048;
+
+__global__ void k_greedy_states(DevSystem sys, GreedyBufs g, GreedyRank r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n2) return;
+    unsigned long long a = ~0ull; unsigned b = ~0u, slot = ~0u;
+    if (i < (unsigned)sys.S * (unsigned)sys.A) {
+        const int s = (int)(i / (unsigned)sys.A), k = (int)(i - (unsigned)s * (unsigned)sys.A);
+        const int n = g.nCand[s];
+        if (k < n) {
+            const float v = g.cand[i].val;
+            const float d = k + 1 < n ? g.cand[i + 1].val - v : 3.40282346638528859811704183484516925e+38f;
+            a = ((unsigned long long)(unsigned)sys.srv_priority[s] << 32) | (unsigned)~f32_sortable(d);
+            b = ~f32_sortable(v);
+            slot = i;
+        }
+    }
+    r.ka[i] = a; r.kb[i] = b; r.kslot[i] = slot;
+}
+
+// (key, state) order: equal keys are laid out in ascending state = ascending server index
+__device__ __forceinline__ bool greedy_rank_less(unsigned long long a1, unsigned b1, unsigned s1, unsigned long long a2, unsigned b2, unsigned s2) {
+    return a1 < a2 || (a1 == a2 && (b1 < b2 || (b1 == b2 && s1 < s2)));
+}
+
+// bitonic stages with partner distance < GREEDY_TILE, in shared memory: for k = kLo..kHi (doubling)
+// the steps j = min(k/2, TILE/2) .. 1
+__global__ void __launch_bounds__(512) k_greedy_bitonic_tile(GreedyRank r, unsigned kLo, unsigned kHi) {
+    __shared__ unsigned long long sa[GREEDY_TILE];
+    __shared__ unsigned sb[GREEDY_TILE];
+    __shared__ unsigned ss[GREEDY_TILE];
+    const unsigned base = blockIdx.x * GREEDY_TILE;
+    for (unsigned i = threadIdx.x; i < GREEDY_TILE; i += 512) { sa[i] = r.ka[base + i]; sb[i] = r.kb[base + i]; ss[i] = r.kslot[base + i]; }
+    __syncthreads();
+    for (unsigned k = kLo; k <= kHi; k <<= 1) {
+        unsigned j0 = k >> 1; if (j0 > GREEDY_TILE / 2) j0 = GREEDY_TILE / 2;
+        for (unsigned j = j0; j > 0; j >>= 1) {
+            for (unsigned idx = threadIdx.x; idx < GREEDY_TILE / 2; idx += 512) {
+                const unsigned i = 2 * (idx & ~(j - 1)) + (idx & (j - 1));
+                const unsigned p = i + j;
+                const bool asc = ((base + i) & k) == 0;
+                const unsigned long long a1 = sa[i], a2 = sa[p]; const unsigned b1 = sb[i], b2 = sb[p], s1 = ss[i], s2 = ss[p];
+                if (greedy_rank_less(a2, b2, s2, a1, b1, s1) == asc && s1 != s2) {
+                    sa[i] = a2; sa[p] = a1; sb[i] = b2; sb[p] = b1; ss[i] = s2; ss[p] = s1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < GREEDY_TILE; i += 512) { r.ka[base + i] = sa[i]; r.kb[base + i] = sb[i]; r.kslot[base + i] = ss[i]; }
+}
+
+// one bitonic step (k, j) with j >= GREEDY_TILE, in global memory
+__global__ void k_greedy_bitonic_step(GreedyRank r, unsigned k, unsigned j) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= r.n2 / 2) return;
+    const unsigned i = 2 * (idx & ~(j - 1)) + (idx & (j - 1));
+    const unsigned p = i + j;
+    const bool asc = (i & k) == 0;
+    const unsigned long long a1 = r.ka[i], a2 = r.ka[p]; const unsigned b1 = r.kb[i], b2 = r.kb[p], s1 = r.kslot[i], s2 = r.kslot[p];
+    if (greedy_rank_less(a2, b2, s2, a1, b1, s1) == asc && s1 != s2) {
+        r.ka[i] = a2; r.ka[p] = a1; r.kb[i] = b2; r.kb[p] = b1; r.kslot[i] = s2; r.kslot[p] = s1;
+    }
+}
+
+// rank of every state
+__global__ void k_greedy_index(GreedyRank r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n2) return;
+    const unsigned slot = r.kslot[i];
+    if (slot != ~0u) r.posOf[slot] = i;
+}
+
+// last rank of a tie group (two or more states with one key), else false; g0/g1 = its range
+__device__ __forceinline__ bool greedy_tie_tail(const GreedyRank& r, unsigned i, unsigned& g0, unsigned& g1) {
+    if (i == 0 || i >= r.n2 || r.kslot[i] == ~0u) return false;
+    const unsigned long long a = r.ka[i]; const unsigned b = r.kb[i];
+    if (i + 1 < r.n2 && r.kslot[i + 1] != ~0u && r.ka[i + 1] == a && r.kb[i + 1] == b) return false;
+    if (!(r.ka[i - 1] == a && r.kb[i - 1] == b)) return false;
+    unsigned j = i - 1;
+    while (j > 0 && r.ka[j - 1] == a && r.kb[j - 1] == b) --j;
+    g0 = j; g1 = i + 1;
+    return true;
+}
+
+// gend[] of every member of a tie group (gend is zeroed before)
+__global__ void k_greedy_tie_groups(GreedyRank r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned g0, g1;
+    if (!greedy_tie_tail(r, i, g0, g1)) return;
+    for (unsigned q = g0; q < g1; ++q) { r.gend[q] = (int)g1; r.gbeg[q] = (int)g0; }
+}
+
+__device__ __forceinline__ int4 greedy_make_rec(const GreedyCand& cd, int priority, int tie, unsigned slot) {
+    int4 v;
+    v.x = (int)(unsigned)((unsigned long long)cd.count & 0xffffffffull);
+    v.y = (int)(unsigned)((unsigned long long)cd.count >> 32);
+    v.z = cd.tf | (priority << 18) | tie;
+    v.w = (int)slot;
+    return v;
+}
+
+// per state: where the following state of the server goes; per rank: the state sorted there
+__global__ void k_greedy_records(DevSystem sys, GreedyBufs g, GreedyRank r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n2) return;
+    const unsigned slot = r.kslot[i];
+    if (slot == ~0u) return;
+    const GreedyCand cd = g.cand[slot];
+    int nx = -1;
+    if (!(cd.tf & GREEDY_LAST)) {
+        const unsigned q = r.posOf[slot + 1];
+        nx = r.gend[q] ? -2 - r.gbeg[q] : (int)q;
+    }
+    r.snext[slot] = nx;
+    r.rec[i] = greedy_make_rec(cd, (int)(r.ka[i] >> 32), r.gend[i] ? GREEDY_TIE : 0, slot);
+    r.nextPos[i] = make_int2(nx, r.gend[i]);
+}
+
+// the initial entries (first candidates) of a tie group take its top ranks in ascending server index
+__global__ void k_greedy_tie_init(DevSystem sys, GreedyBufs g, GreedyRank r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned g0, g1;
+    if (!greedy_tie_tail(r, i, g0, g1)) return;
+    const unsigned A = (unsigned)sys.A;
+    int cnt = 0;
+    for (unsigned q = g0; q < g1; ++q) if (r.kslot[q] % A == 0) ++cnt;
+    const int pr = (int)(r.ka[i] >> 32);
+    int idx = 0;
+    for (unsigned q = g0; q < g1; ++q) {
+        const unsigned slot = r.kslot[q];
+        if (slot % A != 0) continue;
+        const unsigned pos = g1 - (unsigned)cnt + (unsigned)idx++;
+        r.posOf[slot] = pos;
+        r.rec[pos] = greedy_make_rec(g.cand[slot], pr, GREEDY_TIE, slot);
+        r.nextPos[pos] = make_int2(r.snext[slot], (int)g1);
+    }
+    r.top[g1] = cnt;
+}
+
+// 64-ary bitmap over ranks, four levels (up to 2^24 ranks)
+struct GreedyBitmap {
+    unsigned long long* l0; unsigned long long* l1; unsigned long long* l2; unsigned long long* l3;
+    __device__ __forceinline__ int findMin() const {          // -1 when empty
+        const unsigned long long w3 = l3[0];
+        if (!w3) return -1;
+        int i = __ffsll((long long)w3) - 1;
+        i = i * 64 + __ffsll((long long)l2[i]) - 1;
+        i = i * 64 + __ffsll((long long)l1[i]) - 1;
+        i = i * 64 + __ffsll((long long)l0[i]) - 1;
+        return i;
+    }
+    __device__ __forceinline__ void set(int p) {
+        const unsigned long long w = l0[p >> 6];
+        l0[p >> 6] = w | (1ull << (p & 63));
+        if (w) return;                                   // the upper levels already know this word
+        l1[p >> 12] |= 1ull << ((p >> 6) & 63);
+        l2[p >> 18] |= 1ull << ((p >> 12) & 63);
+        l3[0] |= 1ull << ((p >> 18) & 63);
+    }
+    __device__ __forceinline__ void clear(int p) {
+        unsigned long long w = l0[p >> 6] & ~(1ull << (p & 63));
+        l0[p >> 6] = w;
+        if (w) return;
+        w = l1[p >> 12] & ~(1ull << ((p >> 6) & 63));
+        l1[p >> 12] = w;
+        if (w) return;
+        w = l2[p >> 18] & ~(1ull << ((p >> 12) & 63));
+        l2[p >> 18] = w;
+        if (w) return;
+        l3[0] &= ~(1ull << ((p >> 18) & 63));
+    }
+};
+
+__host__ __device__ inline size_t greedy_bitmap_bytes(size_t nStates, size_t* w0, size_t* w1, size_t* w2) {
+    const size_t a = (nStates + 63) / 64, b = (a + 63) / 64, c = (b + 63) / 64;
+    if (w0) *w0 = a; if (w1) *w1 = b; if (w2) *w2 = c;
+    return (a + b + c + 1) * 8;
+}
+
+// SolveGreedy on the ranked queue.  With the priority in the top key bits one queue serves all
+// priority groups: the group boundary (greedy.go:96-103) is where the popped priority changes.
+__global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAllocs pairs, GreedyBufs g, GreedyRank r, int* chosen,
+                                                              int delayedBestEffort, int policy) {
+    extern __shared__ __align__(16) unsigned char greedy_pool[];
+    __shared__ long long avail[256];
+    __shared__ long long usum[256];
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
+    const int A = sys.A;
+    size_t w0, w1, w2;
+    const size_t bmBytes = greedy_bitmap_bytes((size_t)sys.S * A, &w0, &w1, &w2);
+    GreedyBitmap bm;
+    bm.l0 = reinterpret_cast<unsigned long long*>(greedy_pool);
+    bm.l1 = bm.l0 + w0; bm.l2 = bm.l1 + w1; bm.l3 = bm.l2 + w2;
+    GreedyCtx c; c.sys = sys; c.pairs = pairs; c.g = g; c.chosen = chosen; c.avail = avail; c.usum = usum; c.lane = lane;
+    c.pool = greedy_pool + ((bmBytes + 15) & ~(size_t)15);
+    c.g.smemBytes = g.smemBytes - (int)((bmBytes + 15) & ~(size_t)15);
+    for (int t = lane; t < sys.T; t += 32) avail[t] = sys.type_capacity[t];
+    for (size_t i = lane; i < w0 + w1 + w2 + 1; i += 32) bm.l0[i] = 0;
+    __syncwarp();
+    // every server with a candidate starts at its first one (greedy.go:45-73)
+    for (int s = lane; s < sys.S; s += 32)
+        if (g.nCand[s] > 0) {
+            const unsigned p = r.posOf[(size_t)s * A];
+            atomicOr(&bm.l0[p >> 6], 1ull << (p & 63));
+        }
+    __syncwarp();
+    for (size_t i = lane; i < w0; i += 32) if (bm.l0[i]) atomicOr(&bm.l1[i >> 6], 1ull << (i & 63));
+    __syncwarp();
+    for (size_t i = lane; i < w1; i += 32) if (bm.l1[i]) atomicOr(&bm.l2[i >> 6], 1ull << (i & 63));
+    __syncwarp();
+    for (size_t i = lane; i < w2; i += 32) if (bm.l2[i]) atomicOr(&bm.l3[0], 1ull << (i & 63));
+    __syncwarp();
+
+    int curPr = -1;
+    unsigned long long nPops = 0, nFails = 0, cycQueue = 0, cycBest = 0;
+    int nSucc = 0;                       // placements are logged (r.succ) and scattered to chosen[] at the end
+    // lane 0 keeps the bitmap word that holds the minimum in a register (cw, cb): a pop is one
+    // find-first-set unless the word runs empty, and the record of the following set bit is loaded
+    // one iteration ahead.  A server whose placement fails moves to its next candidate; when that
+    // state ranks before everything queued (the usual case: the reference re-inserts it at the
+    // head of the slice) it is simply evaluated next, reading the server's contiguous candidate
+    // records, without going through the queue.
+    int cw = -1; unsigned long long cb = 0;
+    int pfPos = -1; int2 pfNx = make_int2(0, 0); int4 pfRec = make_int4(0, 0, 0, 0);
+    for (;;) {
+        int nUn = 0, more = 0, nextPr = -1;
+        const long long t0 = clock64();
+        if (lane == 0) {
+            for (;;) {
+                if (cb == 0) {
+                    const int m0 = bm.findMin();
+                    if (m0 < 0) break;
+                    cw = m0 >> 6; cb = bm.l0[cw];
+                }
+                const int p = cw * 64 + __ffsll((long long)cb) - 1;
+                int4 rec; int2 nx;
+                if (p == pfPos) { rec = pfRec; nx = pfNx; }
+                else { rec = r.rec[p]; nx = r.nextPos[p]; }
+                const unsigned long long rest = cb & (cb - 1);            // without p
+                if (rest) {
+                    pfPos = cw * 64 + __ffsll((long long)rest) - 1;
+                    pfRec = r.rec[pfPos]; pfNx = r.nextPos[pfPos];
+                } else pfPos = -1;
+                int tf = rec.z;
+                const int pr = (tf >> 18) & 0x7f;
+                if (!delayedBestEffort && pr != curPr) {
+                    if (curPr < 0) curPr = pr;
+                    else { more = 1; nextPr = pr; break; }
+                }
+                ++nPops;
+                // take p out; m = what the queue holds next (-1: nothing)
+                cb = rest;
+                bm.l0[cw] = rest;
+                int m;
+                if (rest) m = pfPos;
+                else {
+                    bm.clear(p);                                          // propagate the empty word upwards
+                    m = bm.findMin();
+                    if (m >= 0) { cw = m >> 6; cb = bm.l0[cw]; }
+                }
+                if (nx.y) r.top[nx.y] = nx.y - p - 1;                     // tie group: p was its lowest occupied rank
+                int state = rec.w, np = nx.x;
+                long long count = (long long)(((unsigned long long)(unsigned)rec.y << 32) | (unsigned)rec.x);
+                for (;;) {
+                    if (tf & GREEDY_SKIP) break;                          // no model / GetAccelerator("") == nil
+                    const int t = tf & 0xffff;
+                    if (avail[t] >= count) {
+                        avail[t] -= count;
+                        r.succ[nSucc++] = state;
+                        break;
+                    }
+                    ++nFails;
+                    if (np == -1) { g.unalloc[nUn++] = state; break; }    // state for now, server below
+                    // does the next state go to the head of the queue?  A tie group hands out the rank
+                    // below its lowest occupied one, so it does as soon as the queue starts inside or
+                    // after the group.
+                    const bool front = m < 0 || (np >= 0 ? np < m : m >= -2 - np);
+                    ++state;
+                    if (front) {
+                        const int4 cd = *reinterpret_cast<const int4*>(g.cand + state);
+                        np = r.snext[state];
+                        count = (long long)(((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x);
+                        tf = cd.w;
+                        continue;
+                    }
+                    int q = np;
+                    if (np < -1) {
+                        const int g1 = r.gend[-2 - np];
+                        const int depth = r.top[g1];
+                        r.top[g1] = depth + 1;
+                        q = g1 - 1 - depth;
+                        r.rec[q] = greedy_make_rec(g.cand[state], pr, GREEDY_TIE, (unsigned)state);
+                        r.nextPos[q] = make_int2(r.snext[state], g1);
+                    }
+                    bm.set(q);                                            // q > m: the cached word stays the minimum's
+                    if ((q >> 6) == cw) cb |= 1ull << (q & 63);
+                    break;
+                }
+            }
+        }
+        nUn = __shfl_sync(0xffffffffu, nUn, 0);
+        more = __shfl_sync(0xffffffffu, more, 0);
+        nextPr = __shfl_sync(0xffffffffu, nextPr, 0);
+        __syncwarp();
+        for (int i = lane; i < nUn; i += 32) g.unalloc[i] = (int)((unsigned)g.unalloc[i] / (unsigned)A);
+        __syncwarp();
+        const long long t1 = clock64();
+        if (!delayedBestEffort || !more) greedy_best_effort(c, g.unalloc, nUn, policy);
+        cycQueue += (unsigned long long)(t1 - t0);
+        cycBest += (unsigned long long)(clock64() - t1);
+        if (!more) break;
+        curPr = nextPr;
+    }
+    nSucc = __shfl_sync(0xffffffffu, nSucc, 0);
+    __syncwarp();
+    for (int i = lane; i < nSucc; i += 32) { const int state = r.succ[i]; chosen[(unsigned)state / (unsigned)A] = state; }
+    if (lane == 0) { g.stats[0] = nPops; g.stats[1] = nFails; g.stats[2] = cycQueue; g.stats[3] = cycBest; }
+}
+
 // copy the chosen candidates out (after best-effort scaling)
-__global__ void k_greedy_collect(DevSystem sys, DevAllocs pairs, const int* __restrict__ chosen_key, int* __restrict__ chosen_acc,
+__global__ void k_greedy_collect(DevSystem sys, DevAllocs pairs, const int* __restrict__ order, const int* __restrict__ chosen_key, int* __restrict__ chosen_acc,
                                  DevAllocs chosen) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sys.S) return;
-    int key = chosen_key[s];
+    const int slot = chosen_key[s];              // s*A + position in the greedy order, or -1
+    const int key = slot >= 0 ? order[slot] : -1;
     chosen_acc[s] = key;
     store_alloc(chosen, (size_t)s, key >= 0 ? load_alloc(pairs, (size_t)s * sys.A + key) : empty_alloc());
 }

@@ -40,17 +40,40 @@ def device_tensor(ptr, n, dtype, device):
     return torch.as_tensor(_CudaView(ptr, n, _TYPESTR[np.dtype(dtype)]), device=device)
 
 
+class TotalsExchange:
+    """The one collective of the unlimited path: every rank all-gathers its 12*T-byte block of
+    partial totals straight from the library's device buffer, then the library sums the blocks in
+    rank order (wva_type_totals_merge) back into that buffer.  Views and the gather buffer are
+    created once."""
+
+    def __init__(self, ctx, n_types, device, stream=None):
+        # the collective is enqueued on the library's own stream, where the partials were produced
+        # and where the merge kernel runs
+        self.ctx, self.T = ctx, int(n_types)
+        self.stream = stream if stream is not None else torch.cuda.ExternalStream(ctx.stream(), device=device)
+        self.world = dist.get_world_size()
+        ptr, nbytes = ctx.type_totals_device()
+        assert nbytes == 12 * self.T
+        self.ptr = ptr
+        self.mine = device_tensor(ptr, nbytes, np.uint8, device)
+        self.gathered = torch.empty(self.world * nbytes, dtype=torch.uint8, device=device)
+        self.count = device_tensor(ptr, self.T, np.int64, device)
+        self.cost = device_tensor(ptr + 8 * self.T, self.T, np.float32, device)
+
+    def __call__(self, sync=True):
+        ptr, _ = self.ctx.type_totals_device()
+        assert ptr == self.ptr, "the library moved its totals buffer"
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.gathered, self.mine)
+        self.ctx.type_totals_merge(self.gathered.data_ptr(), self.world)
+        if sync:
+            self.stream.synchronize()
+        return self.count, self.cost
+
+
 def allreduce_totals_device(ctx, n_types, device, stream=None):
-    """The one collective of the unlimited path, in place on the library's totals buffer."""
-    ptr, _ = ctx.type_totals_device()
-    cnt = device_tensor(ptr, n_types, np.int64, device)
-    cst = device_tensor(ptr + 8 * n_types, n_types, np.float32, device)
-    if stream is not None:
-        with torch.cuda.stream(stream):
-            dist.all_reduce(cnt); dist.all_reduce(cst)
-    else:
-        dist.all_reduce(cnt); dist.all_reduce(cst)
-    return cnt, cst
+    """One-shot form of TotalsExchange."""
+    return TotalsExchange(ctx, n_types, device, stream)()
 
 
 def allreduce_totals_host(count, cost):
@@ -88,9 +111,14 @@ def gather_pair_rows_device(ctx, n_servers, n_accels, world, device):
     n = n_servers * n_accels
     bounds = [shard_range(n_servers, r, world) for r in range(world)]
     rank = dist.get_rank()
+    even = len({c for _, c in bounds}) == 1
+    f0, c0 = bounds[rank]
     for name, (ptr, dt) in ptrs.items():
         full = device_tensor(ptr, n, dt, device)
-        for r, (f, c) in enumerate(bounds):          # shards may differ by one server: broadcast per owner, in place
-            if c:
-                dist.broadcast(full[f * n_accels:(f + c) * n_accels], src=r)
+        if even:                                     # equal shards: one in-place all-gather per field
+            dist.all_gather_into_tensor(full, full[f0 * n_accels:(f0 + c0) * n_accels])
+        else:
+            for r, (f, c) in enumerate(bounds):      # shards differ by one server: broadcast per owner, in place
+                if c:
+                    dist.broadcast(full[f * n_accels:(f + c) * n_accels], src=r)
     ctx.pairs_commit()

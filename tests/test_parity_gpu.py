@@ -213,11 +213,15 @@ def test_solve_unlimited_and_totals(wva, oracle, ctx):
 
 @pytest.mark.parametrize("policy", [0, 1, 2, 3])
 @pytest.mark.parametrize("delayed", [False, True])
-def test_solve_greedy_policies(wva, oracle, ctx, policy, delayed):
+@pytest.mark.parametrize("ranked", [1, 0])
+def test_solve_greedy_policies(wva, oracle, ctx, policy, delayed, ranked):
     img, pairs, feas = _capacity_case(wva, oracle, 52, 500, 6, 3, 0.6)
     ctx.upload(img)
     ctx.analyze_pairs(download=False)
+    ctx.solve_set_ranked(ranked)
     acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
+    assert ctx.solve_greedy_path() == (2 if ranked else 1)
+    ctx.solve_set_ranked(1)
     w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
     assert np.array_equal(acc, w_acc)
     _assert_allocs_equal(chosen, w_chosen)
@@ -241,13 +245,42 @@ def test_solve_greedy_ties(wva, oracle, ctx):
     assert feas.reshape(img.S, img.A).any(axis=1).all() and feas.sum() >= 2 * img.S
     acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
     wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.45)
-    for policy in (0, 1, 3):
+    for policy, ranked in ((0, 1), (1, 1), (2, 1), (3, 1), (1, 0), (3, 0)):
         ctx.upload(img)
         ctx.analyze_pairs(download=False)
+        ctx.solve_set_ranked(ranked)
         acc, chosen = ctx.solve(unlimited=False, policy=policy)
+        path = ctx.solve_greedy_path()
+        ctx.solve_set_ranked(1)
+        assert path == (2 if ranked else 1)          # ranked: every key ties, the tie-group stacks carry the recency order
         w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, policy=policy)
         assert np.array_equal(acc, w_acc)
         _assert_allocs_equal(chosen, w_chosen)
+
+
+@pytest.mark.parametrize("policy,delayed,ranked", [(1, False, 1), (3, True, 1), (2, False, 1), (0, True, 1), (3, True, 0), (1, False, 0)])
+def test_solve_greedy_large(wva, oracle, ctx, policy, delayed, ranked):
+    """12 000 servers: the delayed-best-effort queue no longer fits shared memory (global-memory
+    heap), the per-priority groups do.  Candidates come from the CUDA path (pair parity is
+    covered above); the assignment is compared with the oracle's."""
+    img = wva.synth.make_system(12000, 4, seed=57, n_types=3)
+    ctx.upload(img)
+    pairs, feas = ctx.analyze_pairs()
+    acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
+    wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.55)
+    ctx.upload(img)
+    ctx.analyze_pairs(download=False)
+    ctx.solve_set_ranked(ranked)
+    acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
+    path = ctx.solve_greedy_path()
+    ctx.solve_set_ranked(1)
+    w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
+    assert np.array_equal(acc, w_acc)
+    _assert_allocs_equal(chosen, w_chosen)
+    assert path == (2 if ranked else 1)
+    count, cost = ctx.allocate_by_type()
+    assert (count <= img.type_capacity).all()
+    assert (acc < 0).any() or policy != 0
 
 
 def test_overlapped_analyze_equals_separate_calls(wva, oracle, ctx):
