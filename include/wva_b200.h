@@ -252,8 +252,9 @@ int wva_pair_steps(wva_ctx* ctx, uint64_t* steps);
 /* warp-per-pair kernel counters: {chain steps, sum of bisection rounds over pairs, max rounds of a pair,
  * trailing-Analyze evaluations that the cache / guess did not cover (+100 per missed guess)}. */
 int wva_pair_counters(wva_ctx* ctx, uint64_t out[4]);
-/* With wva_pairs_set_pstore(ctx, 4) set before wva_analyze_pairs: per pair of the shard, SM cycles spent
- * and (rounds << 32) | rounds-with-evaluations of the warp-per-pair kernel (profiling aid). */
+/* With wva_pairs_set_pstore(ctx, 4) set before wva_analyze_pairs: per pair of the shard two words
+ * (profiling aid): [0] = SM cycles (bits 0-35) | exact re-evaluations of uncertain speculative nodes
+ * (bits 36-43) | chain steps / 1024 (bits 44-63); [1] = (rounds << 32) | rounds-with-evaluations. */
 int wva_pair_debug(wva_ctx* ctx, uint64_t* out, int32_t n_pairs);
 
 /* ---- Optimize ------------------------------------------------------------ */

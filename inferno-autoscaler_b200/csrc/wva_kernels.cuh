@@ -307,7 +307,8 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
              int smemEntriesPerWarp, double* pbuf, long long pbufStrideK, unsigned long long* dbg) {
     extern __shared__ __align__(16) unsigned char pairs_smem[];
     const long long tStart = clock64();
-    int activeRounds = 0, totalRounds = 0;
+    int activeRounds = 0, totalRounds = 0, pendEvals = 0;
+    long long solveCycles = 0;
     const int pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp-uniform
     const int lane = threadIdx.x & 31;
     if (pid >= nPairs) return;
@@ -404,7 +405,9 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
             if (__any_sync(0xffffffffu, act)) ++activeRounds;
             ++totalRounds;
             // tree nodes are speculative (certOnly); the two boundary evaluations are needed for sure
+            const long long tw0 = clock64();
             bool solved = warp_solve(wp, act, x, st, steps, valid, node > 0, unc);
+            solveCycles += clock64() - tw0;
             if (act && !unc) lastX = x;
             if (__any_sync(0xffffffffu, act && !solved)) { toSlow = true; break; }
             float y = act && valid && !unc ? eval_y(wp, half, st) : 0.0f;
@@ -462,7 +465,7 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
                     // exact evaluation of the pending node(s): the lane that owns node `cur` of a pending half-warp
                     const bool mine = pend && (hl == (first ? cur + 1 : cur));
                     bool v2, u2;
-                    ++activeRounds;
+                    ++activeRounds; ++pendEvals;
                     bool solved2 = warp_solve(wp, mine, x, st, steps, v2, false, u2);
                     if (__any_sync(0xffffffffu, mine && !solved2)) { slowExit = true; break; }
                     if (mine) { valid = v2; unc = false; lastX = x; y = v2 ? eval_y(wp, half, st) : 0.0f; }
@@ -542,8 +545,14 @@ k_pairs_warp(DevSystem sys, int s0, int nPairs, const long long* __restrict__ ta
 
     if (ok) rec.value = transition_penalty(sys.srv_cur_acc[s], sys.srv_cur_replicas[s], sys.srv_cur_cost[s], rec.acc,
                                            rec.numReplicas, rec.cost);
-    if (dbg && lane == 0) { dbg[2 * pid] = (unsigned long long)(clock64() - tStart); dbg[2 * pid + 1] = ((unsigned long long)totalRounds << 32) | (unsigned)activeRounds; }
+    const unsigned long long tEnd = clock64();
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+    if (dbg && lane == 0) {
+        // word 0: cycles (36 bits) | exact re-evaluations of uncertain nodes (8 bits) << 36 | chain steps / 1024 (20 bits) << 44
+        unsigned long long ks = (unsigned long long)solveCycles >> 10; if (ks > 0xfffffull) ks = 0xfffffull;
+        dbg[2 * pid] = ((tEnd - tStart) & 0xfffffffffull) | ((unsigned long long)(pendEvals & 0xff) << 36) | (ks << 44);
+        dbg[2 * pid + 1] = ((unsigned long long)totalRounds << 32) | (unsigned)activeRounds;
+    }
     if (lane == 0) {
         if (toSlow) { ok = false; slow_list[atomicAdd(slow_count, 1)] = pid; }
         if (!ok) rec = empty_alloc();

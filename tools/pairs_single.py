@@ -17,4 +17,4 @@ for cert in (1, 0):
                 ctx.analyze_pairs(download=False); ts.append(ctx.phase_usec(wva.abi.PHASE_PAIRS))
             d = ctx.pair_debug()[0]
             print("cert %d %s N %3d: phase usec min %d kernel cycles %d (%.3f ms) rounds %d active %d %s" % (
-                cert, "hbm " if knob & 2 else "smem", mb, min(ts), d[0], d[0] / 1.965e6, int(d[1]) >> 32, int(d[1]) & 0xffffffff, ctx.pair_counters()), flush=True)
+                cert, "hbm " if knob & 2 else "smem", mb, min(ts), int(d[0]) & 0xfffffffff, (int(d[0]) & 0xfffffffff) / 1.965e6, int(d[1]) >> 32, int(d[1]) & 0xffffffff, ctx.pair_counters()), flush=True)
