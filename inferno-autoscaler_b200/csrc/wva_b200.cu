@@ -572,14 +572,36 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     // certified tails on: one thread per (server, accelerator, replicas) row with a shared ramp (k_grid_rows);
     // off: one thread per candidate (k_grid)
     // (the row kernel needs >= 32 K rows to fill the machine: each thread walks its row's batch sizes serially)
-    const bool rowsMode = ctx->certified && ctx->grid_rows && (ctx->grid_rows == 2 || slicePairsMax * (size_t)r_max >= 32768);
+    // Shards with few rows split every pair over n_bseg blocks of b_seg batch sizes (>= 32 each) so that
+    // about 64 K threads exist; below 16 K threads the per-candidate kernel is used.
+    gp.n_bseg = 1; gp.b_seg = b_max;
+    {
+        const size_t rows = slicePairsMax * (size_t)r_max;
+        if (rows > 0 && rows < 65536) {
+            int want = (int)((65536 + rows - 1) / rows);
+            const int maxSeg = b_max / 32 > 0 ? b_max / 32 : 1;
+            if (want > maxSeg) want = maxSeg;
+            gp.b_seg = (b_max + want - 1) / want;
+            gp.n_bseg = (b_max + gp.b_seg - 1) / gp.b_seg;
+        }
+    }
+    // (measured on config 2, 8 192 rows x 8 segments: row kernel 0.47 ms + 0.45 ms for the 356 candidates whose
+    // certificate is ambiguous -- the exact chain of one b = 512 candidate is 11 264 dependent steps -- against
+    // 0.55 ms for the per-candidate kernel, which finishes such chains inline while other warps work; so
+    // segmentation is used only when asked for)
+    const bool rowsMode = ctx->certified && ctx->grid_rows &&
+                          (ctx->grid_rows == 2 || slicePairsMax * (size_t)r_max >= 32768);
+    if (!(rowsMode && ctx->grid_rows == 2)) { gp.n_bseg = 1; gp.b_seg = b_max; }
     const size_t smem = (size_t)b_max * 20;
     if (smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (slicePairsMax * (size_t)gp.n_rchunks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
-    CK(ctx->blockSlot.ensure((slicePairsMax * (size_t)gp.n_rchunks + 1) * sizeof(GridSlot)));
+    {
+        const size_t perPairBlocks = (size_t)(gp.n_rchunks > gp.n_bseg ? gp.n_rchunks : gp.n_bseg);
+        CK(ctx->blockSlot.ensure((slicePairsMax * perPairBlocks + 1) * sizeof(GridSlot)));
+    }
     gp.block_slot = ctx->blockSlot.as<GridSlot>();
     const long long stride = 11LL * b_max + 1;
 
@@ -600,7 +622,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     for (int sBeg = 0; sBeg < ns; sBeg += srvPerSlice) {
         const int sCnt = (ns - sBeg) < srvPerSlice ? (ns - sBeg) : srvPerSlice;
         const size_t slicePairs = (size_t)sCnt * A;
-        const size_t nBlocks = rowsMode ? slicePairs : slicePairs * (size_t)gp.n_rchunks;
+        const size_t nBlocks = rowsMode ? slicePairs * (size_t)gp.n_bseg : slicePairs * (size_t)gp.n_rchunks;
         gp.pair_base = sBeg * A;
         int counts[2] = {0, 0};
         int slow = 0, heavy = 0;

@@ -597,6 +597,7 @@ struct GridSlot { unsigned long long key; float cost, itl, ttft, rho; int sl; in
 struct GridParams {
     int r_max, b_max;
     int r_chunk, n_rchunks;          // replicas per block / blocks per pair
+    int b_seg, n_bseg;               // row kernel: batch sizes per block / blocks per pair
     int s0, ns;                      // shard
     int pair_base;                   // (server, accelerator) pairs of the shard that precede the slice being swept
     wva_metrics* cube;               // [ns*A*r_max*b_max] or nullptr
@@ -883,6 +884,10 @@ k_grid(DevSystem sys, GridParams gp) {
 // window left) is appended to the deferred list and evaluated by the exact chain in k_grid_list.
 // Lanes of a warp hold consecutive r of the same pair: they step n together, so the shared-memory
 // table reads are broadcasts.
+// Small shards have too few rows to fill the machine: a pair is then split over n_bseg blocks, block
+// `seg` evaluating the batch sizes (seg*b_seg, (seg+1)*b_seg] of every row after running the ramp up
+// to seg*b_seg without evaluating anything (the ramp is a few instructions per step, a candidate a
+// few hundred).
 // ---------------------------------------------------------------------------------------
 #define WVA_ROWS_THREADS 64
 __global__ void __launch_bounds__(WVA_ROWS_THREADS)
@@ -895,15 +900,17 @@ k_grid_rows(DevSystem sys, GridParams gp) {
     __shared__ unsigned long long sh_key;
     __shared__ unsigned long long sh_cnt[3];
 
-    const int pairSlice = blockIdx.x;
+    const int pairSlice = blockIdx.x / gp.n_bseg, seg = blockIdx.x % gp.n_bseg;
     const int pairLocal = gp.pair_base + pairSlice;
     const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
     const int s = gp.s0 + sl;
     const int B = gp.b_max, R = gp.r_max;
+    const int b0 = seg * gp.b_seg;                                   // this block: states b0+1 .. b1
+    const int b1 = (b0 + gp.b_seg < B) ? b0 + gp.b_seg : B;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
+        sh_nGood = b1; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
         gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
     }
     const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
@@ -918,8 +925,10 @@ k_grid_rows(DevSystem sys, GridParams gp) {
     const size_t candBase = ((size_t)pairLocal * R) * (size_t)B;
     if (blockStatus != WVA_CAND_OK) {
         if (gp.status || gp.cube) {
-            const size_t n = (size_t)R * B;
-            for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const int w = b1 - b0;
+            const size_t n = (size_t)R * w;
+            for (size_t j = threadIdx.x; j < n; j += blockDim.x) {
+                const size_t i = (j / w) * (size_t)B + (size_t)b0 + (j % w);
                 if (gp.status) gp.status[candBase + i] = (unsigned char)blockStatus;
                 if (gp.cube) { float4 z = make_float4(0, 0, 0, 0); float4* c = reinterpret_cast<float4*>(&gp.cube[candBase + i]); c[0] = z; c[1] = z; }
             }
@@ -929,13 +938,13 @@ k_grid_rows(DevSystem sys, GridParams gp) {
     __syncthreads();
     ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
     double2* gtab = gp.pair_tab + (size_t)pairSlice * B;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    for (int i = threadIdx.x; i < b1; i += blockDim.x) {
         float r = sf.rate(i + 1);
         rateF[i] = r;
         double d = (double)r;
         double y = rcp_refined(d);
         rateD[i] = d; rcp[i] = y;
-        gtab[i] = make_double2(d, y);
+        if (i >= b0) gtab[i] = make_double2(d, y);                  // each block publishes its own part
         if (!(r > 0.0f) || !(r < CUDART_INF_F)) atomicMin(&sh_nGood, i);
     }
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
@@ -962,7 +971,7 @@ k_grid_rows(DevSystem sys, GridParams gp) {
         bool stopped = false;        // ramp died out: sums frozen
         bool broken = !lamOk;        // chain left the value window (or bad table entry): rest of the row goes to the exact kernels
         const size_t rowBase = candBase + (size_t)(r - 1) * B;
-        for (int n = 0; n < B; ++n) {
+        for (int n = 0; n < b1; ++n) {
             const int b = n + 1;
             // ---- one step of the shared ramp: state b ----
             if (!stopped && !broken) {
@@ -1003,6 +1012,7 @@ k_grid_rows(DevSystem sys, GridParams gp) {
                 }
             }
             // ---- candidate (r, b) ----
+            if (n < b0) continue;                                    // another block's batch sizes
             const size_t ci = rowBase + (size_t)n;
             const int K = 11 * b;
             const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
