@@ -113,7 +113,9 @@ def test_config3_pairs_sample(wva, oracle, ctx):
     assert np.array_equal(gfe, gfe_x) and got.equal_bits(got_x)[0]
     ctx.analyze_pairs(download=False)
     rng = np.random.default_rng(3)
-    pick = np.sort(rng.choice(img.S, 40, replace=False))
+    # server 628 holds a pair whose chain spans more than 1000 binades (p[n]/sum subnormal for part of
+    # pass 2: the IEEE-division elements of pass2_run)
+    pick = np.unique(np.concatenate([rng.choice(img.S, 40, replace=False), [628]]))
     for s in pick:
         sub = img.shard(int(s), 1)
         want, wfe, _ = oracle.analyze_pairs(sub)

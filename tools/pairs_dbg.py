@@ -5,7 +5,9 @@ import wva_import
 wva = wva_import.load()
 from inferno_autoscaler_b200 import binding
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-img = wva.synth.make_system(S, 4, seed=2, n_types=4)
+A = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+img = wva.synth.make_system(S, A, seed=seed, n_types=A)
 ctx = binding.Context(0)
 ctx.upload(img); ctx.pairs_set_pstore(4)
 for i in range(2): ctx.analyze_pairs(download=False)
