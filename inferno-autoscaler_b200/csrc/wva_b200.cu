@@ -5,8 +5,10 @@
 #include "wva_kernels.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -52,8 +54,51 @@ struct PinnedBuf {
 
 }  // namespace
 
+// One helper thread per context: runs the candidate sweep's host side while the calling thread
+// drives the pair sizing (both have stream synchronisations in the middle).
+struct SweepWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has = false, done = false, quit = false;
+    void start() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has || quit; });
+                if (quit) return;
+                std::function<void()> j = std::move(job);
+                has = false;
+                lk.unlock();
+                j();
+                lk.lock();
+                done = true;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> j) {
+        { std::lock_guard<std::mutex> lk(m); job = std::move(j); has = true; done = false; }
+        cv.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return done; }); }
+    void stop() {
+        if (!th.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv.notify_all();
+        th.join();
+    }
+};
+
 struct wva_ctx {
     int device = 0;
+    SweepWorker worker;
+    // host-side plan of the per-pair service-rate tables of k_pairs_warp: an upper bound of every pair's
+    // N from the uploaded image (pair_batch_size without the validity tests), offsets for the shard
+    std::vector<long long> hostN;
+    bool plan_valid = false;
+    long long plan_total = 0, plan_maxN = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t gstream = nullptr;      // the candidate sweep has its own stream so it can overlap the pair sizing
     cudaEvent_t evg0 = nullptr, evg1 = nullptr, evJoin = nullptr, evFork = nullptr;
@@ -216,6 +261,7 @@ int wva_ctx_create(int device, wva_ctx** out) {
 
 void wva_ctx_destroy(wva_ctx* ctx) {
     if (!ctx) return;
+    ctx->worker.stop();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
@@ -296,6 +342,28 @@ int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
     ds.srv_cur_acc = (const int*)(d + o_sca); ds.srv_cur_replicas = (const int*)(d + o_scr); ds.srv_cur_cost = (const float*)(d + o_scc);
     ctx->S = S; ctx->A = A; ctx->M = M; ctx->T = T;
     ctx->s0 = 0; ctx->ns = S;
+    // N of CreateAllocation (allocation.go:77-87) per pair, or an upper bound where the device finds the
+    // pair unusable (it then needs no table at all): sizes the tables of the warp-per-pair kernel without
+    // a device round trip
+    ctx->hostN.assign((size_t)S * A, 0);
+    for (int s = 0; s < S; ++s) {
+        const int m = h->srv_model[s];
+        const long long outTok = h->srv_out_tokens[s];
+        if (h->srv_arrival_rpm[s] == 0.0f || outTok == 0) continue;
+        for (int a = 0; a < A; ++a) {
+            long long n;
+            if (h->srv_max_batch[s] > 0) n = h->srv_max_batch[s];
+            else if (m < 0) n = 0;
+            else {
+                const size_t pi = (size_t)m * A + a;
+                const long long prod = (long long)((unsigned long long)(long long)h->perf_max_batch[pi] * (unsigned long long)(long long)h->perf_at_tokens[pi]);
+                n = (outTok == -1) ? (long long)(0ull - (unsigned long long)prod) : prod / outTok;
+                if (n < 1) n = 1;
+            }
+            ctx->hostN[(size_t)s * A + a] = n;
+        }
+    }
+    ctx->plan_valid = false;
     ctx->have_system = true;
     ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
     timer.stop();
@@ -307,6 +375,7 @@ int wva_set_shard(wva_ctx* ctx, int32_t first, int32_t count) {
     if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
     if (first < 0 || count < 0 || first + count > ctx->S) return fail(ctx, WVA_EINVAL, "shard out of range");
     ctx->s0 = first; ctx->ns = count;
+    ctx->plan_valid = false;
     ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
     return WVA_OK;
 }
@@ -329,25 +398,28 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
     CK(cudaMemsetAsync(ctx->stepCounter.p, 0, 32, ctx->stream));
     int slow = 0;
     if (nPairs > 0) {
-        k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
-        LAUNCH_CHECK();
         if (nPairs <= ctx->pairs_warp_max) {
-            // latency-oriented variant: one warp per pair, per-pair {rate, reciprocal} tables in HBM
-            std::vector<long long> nHost((size_t)nPairs), offs((size_t)nPairs);
-            CK(cudaMemcpyAsync(nHost.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            long long total = 0, maxN = 0;
-            const long long budget = (2LL << 30) / 16;          // at most 2 GB of tables
-            for (int i = 0; i < nPairs; ++i) {
-                long long N = nHost[(size_t)i];
-                if (N > maxN && N <= (1LL << 26)) maxN = N;
-                if (N <= 0) { offs[(size_t)i] = 0; continue; }   // pair does no queueing work: offset unused
-                if (N > (1LL << 26) || total + N > budget) { offs[(size_t)i] = -1; continue; }
-                offs[(size_t)i] = total; total += N;
+            // latency-oriented variant: one warp per pair, per-pair {rate, reciprocal} tables in HBM; the table
+            // plan comes from the host copy of N (made at upload) and is kept while image and shard stay
+            if (!ctx->plan_valid) {
+                std::vector<long long> offs((size_t)nPairs);
+                long long total = 0, maxN = 0;
+                const long long budget = (2LL << 30) / 16;          // at most 2 GB of tables
+                const long long* nHost = ctx->hostN.data() + (size_t)ctx->s0 * A;
+                for (int i = 0; i < nPairs; ++i) {
+                    long long N = nHost[(size_t)i];
+                    if (N > maxN && N <= (1LL << 26)) maxN = N;
+                    if (N <= 0) { offs[(size_t)i] = 0; continue; }   // pair does no queueing work: offset unused
+                    if (N > (1LL << 26) || total + N > budget) { offs[(size_t)i] = -1; continue; }
+                    offs[(size_t)i] = total; total += N;
+                }
+                CK(ctx->pairTabs.ensure((size_t)(total ? total : 1) * 16));
+                CK(ctx->pairTabOff.ensure((size_t)nPairs * 8));
+                CK(cudaMemcpyAsync(ctx->pairTabOff.p, offs.data(), (size_t)nPairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));               // offs is a local
+                ctx->plan_total = total; ctx->plan_maxN = maxN; ctx->plan_valid = true;
             }
-            CK(ctx->pairTabs.ensure((size_t)(total ? total : 1) * 16));
-            CK(ctx->pairTabOff.ensure((size_t)nPairs * 8));
-            CK(cudaMemcpyAsync(ctx->pairTabOff.p, offs.data(), (size_t)nPairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+            const long long maxN = ctx->plan_maxN;
             const int warpsPerBlock = WVA_PAIRS_WARP_THREADS / 32;
             // shared-memory tables: up to 3072 entries (48 KB) per warp, 4 warps per block
             int smemEntries = ctx->pairs_smem ? (int)(maxN < 3072 ? maxN : 3072) : 0;
@@ -369,6 +441,8 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
                 ctx->pairs_debug ? ctx->pairDbg.as<unsigned long long>() : nullptr);
             LAUNCH_CHECK();
         } else {
+        k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
+        LAUNCH_CHECK();
         const int* order = nullptr;
         if (nPairs > 1024) {
             // order pairs by chain length (bucket = bit length of N, heaviest first) so that the lanes
@@ -403,7 +477,10 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
         std::vector<int> list((size_t)slow);
         CK(cudaMemcpy(list.data(), ctx->slowList.p, (size_t)slow * 4, cudaMemcpyDeviceToHost));
         std::vector<long long> nAllPairs((size_t)nPairs);
-        CK(cudaMemcpy(nAllPairs.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost));
+        k_pair_batch<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, ctx->s0, nPairs, ctx->pairN.as<long long>());
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(nAllPairs.data(), ctx->pairN.p, (size_t)nPairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         std::vector<long long> offs((size_t)slow);
         long long total = 0;
         for (int i = 0; i < slow; ++i) {
@@ -744,9 +821,10 @@ int wva_analyze(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube) {
     CK(cudaStreamWaitEvent(ctx->gstream, ctx->evFork, 0));
     int rcGrid = WVA_OK;
     const int dev = ctx->device;
-    std::thread sweep([&] { cudaSetDevice(dev); rcGrid = grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0, false); });
+    if (!ctx->worker.th.joinable()) ctx->worker.start();
+    ctx->worker.submit([&] { cudaSetDevice(dev); rcGrid = grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0, false); });
     int rcPairs = wva_analyze_pairs(ctx, nullptr, nullptr);
-    sweep.join();
+    ctx->worker.wait();
     // join: later work on the main stream sees the sweep's results
     CK(cudaEventRecord(ctx->evJoin, ctx->gstream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));

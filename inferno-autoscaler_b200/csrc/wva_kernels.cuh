@@ -889,8 +889,8 @@ k_grid(DevSystem sys, GridParams gp) {
 // to seg*b_seg without evaluating anything (the ramp is a few instructions per step, a candidate a
 // few hundred).
 // ---------------------------------------------------------------------------------------
-#define WVA_ROWS_THREADS 64
-__global__ void __launch_bounds__(WVA_ROWS_THREADS)
+#define WVA_ROWS_THREADS 32
+__global__ void __launch_bounds__(WVA_ROWS_THREADS, 16)
 k_grid_rows(DevSystem sys, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* rateD = reinterpret_cast<double*>(smem_raw);
