@@ -234,9 +234,10 @@ int wva_pairs_commit(wva_ctx* ctx);
  * constant-rate tail are first evaluated from the exact ramp plus the geometric closed form and accepted
  * only when every float32 rounding of the result is unambiguous within a proven error bound; otherwise
  * the exact chain runs.  Results are identical either way; default on (1).  With certified tails the
- * sweep uses one thread per (server, accelerator, replicas) row sharing one ramp across batch sizes;
- * chosen automatically when the shard has >= 32 K rows.  on = 3: always one thread per candidate;
- * on = 5: always one thread per row (tuning / A-B). */
+ * candidates of a (server, accelerator, replicas) row share one ramp across batch sizes when the
+ * shard has >= 32 K rows (one thread per row); smaller shards use one thread per candidate.
+ * on = 3: always one thread per candidate; on = 5: always one thread per row; on = 9: one warp per
+ * row with lanes = batch sizes (tuning / A-B; all bit-identical). */
 int wva_set_certified_tails(wva_ctx* ctx, int32_t on);
 /* Tuning: shards with at most max_pairs (server, accelerator) pairs use the warp-per-pair kernel
  * (speculative bisection, lowest latency); larger shards use one thread per pair (highest

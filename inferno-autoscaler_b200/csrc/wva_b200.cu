@@ -133,6 +133,7 @@ struct wva_ctx {
     DevBuf totals;
     DevBuf greedyBuf;
     bool greedy_attr = false;
+    int grid_list_warp = 1;     // deferred sweep chains: one warp per chain when the list is short
     int greedy_ranked = 1;      // 0: always the heap kernel
     int greedy_path = 0;        // last limited solve: 1 heap, 2 ranked queue
     uint64_t greedy_stats[4] = {0, 0, 0, 0};
@@ -534,7 +535,8 @@ int wva_pairs_commit(wva_ctx* ctx) {
 int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
     if (!ctx) return WVA_EINVAL;
     ctx->certified = (on & 1) ? 1 : 0;
-    ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : 1);      // bit 1: always one thread per candidate; bit 2: always one thread per row
+    // bit 1: always one thread per candidate; bit 2: always one thread per row; bit 3: always one warp per row
+    ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : ((on & 8) ? 3 : 1));
     ctx->dsys.cert = ctx->certified;
     return WVA_OK;
 }
@@ -629,6 +631,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     // with certified tails almost no chain runs a long exact tail any more: finishing the few that do
     // inside the sweep kernel is cheaper than a second kernel + host round trip (cap < 0 = automatic)
     gp.tail_cap = ctx->grid_tail_cap >= 0 ? ctx->grid_tail_cap : (ctx->certified ? 0 : 192);
+
     gp.slow_count = ctx->gridSlowCount.as<int>();
     gp.heavy_count = ctx->gridSlowCount.as<int>() + 1;
 
@@ -666,14 +669,27 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     // certificate is ambiguous -- the exact chain of one b = 512 candidate is 11 264 dependent steps -- against
     // 0.55 ms for the per-candidate kernel, which finishes such chains inline while other warps work; so
     // segmentation is used only when asked for)
-    const bool rowsMode = ctx->certified && ctx->grid_rows &&
+    const bool rowsMode = ctx->certified && ctx->grid_rows && ctx->grid_rows != 3 &&
                           (ctx->grid_rows == 2 || slicePairsMax * (size_t)r_max >= 32768);
     if (!(rowsMode && ctx->grid_rows == 2)) { gp.n_bseg = 1; gp.b_seg = b_max; }
+    // one warp per row (k_grid_wrow), 8 rows per block: only when asked for.  Measured on config 2 (8 192 rows):
+    // 0.33 ms for the rows + 0.38 ms for the 356 candidates whose certificate is ambiguous (k_grid_list_warp;
+    // the phase lasts as long as its slowest exact chain) against 0.67 ms for k_grid on the same box, which
+    // runs those chains inline while other warps work.
+    const bool wrowMode = ctx->certified && !rowsMode && ctx->grid_rows == 3 &&
+                          (size_t)b_max * 20 + 16 + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8 <= 200 * 1024;
+    if (wrowMode) {
+        gp.r_chunk = WVA_GRID_THREADS / 32;
+        gp.n_rchunks = (r_max + gp.r_chunk - 1) / gp.r_chunk;
+    }
     const size_t smem = (size_t)b_max * 20;
     if (smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    // k_grid_wrow: the table, then per warp the checkpoints and the quotient buffer of warp_exact
+    const size_t smemW = align_up(smem, 16) + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8;
+    if (smemW > 48 * 1024) CK(cudaFuncSetAttribute(k_grid_wrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
     if (slicePairsMax * (size_t)gp.n_rchunks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
     {
         const size_t perPairBlocks = (size_t)(gp.n_rchunks > gp.n_bseg ? gp.n_rchunks : gp.n_bseg);
@@ -708,6 +724,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
             CK(cudaEventRecord(ctx->evk0, ctx->gstream));
             if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
+            else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);
             else k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
             CK(cudaEventRecord(ctx->evk1, ctx->gstream));
@@ -736,7 +753,17 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
                     LAUNCH_CHECK();
                     order = ctx->heavyOrder.as<int>();
                 }
-                k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, order, heavy, nullptr, 0, 0);
+                // few chains: the phase lasts as long as ONE exact chain -- one warp per chain (cooperative pass 2);
+                // many: one thread per chain, ordered by length
+                const size_t smemLW = (size_t)WVA_LISTW_WARPS * (2 * (size_t)b_max + WVA_WX_CP + 1 + 1024) * 8;
+                if (heavy <= 4096 && smemLW <= 200 * 1024 && ctx->grid_list_warp) {
+                    if (smemLW > 48 * 1024)
+                        CK(cudaFuncSetAttribute(k_grid_list_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemLW));
+                    k_grid_list_warp<<<(heavy + WVA_LISTW_WARPS - 1) / WVA_LISTW_WARPS, WVA_LISTW_WARPS * 32, smemLW, ctx->gstream>>>(
+                        ctx->dsys, gp, gp.heavy_list, heavy, 0);
+                } else {
+                    k_grid_list<<<(heavy + 127) / 128, 128, 0, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, order, heavy, nullptr, 0, 0);
+                }
                 LAUNCH_CHECK();
                 CK(cudaEventRecord(ctx->evh1, ctx->gstream));
                 CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 4, cudaMemcpyDeviceToHost, ctx->gstream));

@@ -1126,6 +1126,374 @@ k_grid_rows(DevSystem sys, GridParams gp) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_grid_wrow: the sweep with ONE WARP PER ROW (server, accelerator, replicas) -- shards too small for
+// one thread per row.  As in k_grid_rows the row's candidates share one ramp; here all 32 lanes run
+// it in lockstep (same values in every lane) and lane l keeps the state (p[b], sum, sum i p[i]) of
+// its own batch size b = 32 c + l + 1; after every 32 steps the lanes evaluate their 32 candidates
+// together (certified closed-form tail, or the row's frozen exact sums once the ramp has died out).
+// Against one thread per candidate (k_grid) a row costs one ramp of B steps instead of one per
+// 32-candidate item (B/32 ramps of growing length).  A candidate whose certificate fails needs the
+// exact chain (2 x 11 b dependent steps); such candidates cluster -- the aggregates of one row
+// converge as b grows, so if the limit sits on a float32 rounding boundary every large b of that row
+// is ambiguous -- hence they are not run where they are found (one warp would run them one after the
+// other) but deferred to the list kernels, which spread them over the whole GPU (k_grid_list_warp:
+// one warp per chain).  Should that list be full, a block-local list is evaluated by the block's
+// warps afterwards.
+// Block = (pair, chunk of replica counts); warps pull rows from a shared counter.
+// ---------------------------------------------------------------------------------------
+#define WVA_WROW_LIST 2048
+__global__ void __launch_bounds__(WVA_GRID_THREADS, 2)
+k_grid_wrow(DevSystem sys, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* rateD = reinterpret_cast<double*>(smem_raw);
+    double* rcp = rateD + gp.b_max;
+    float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
+    __shared__ int sh_item, sh_nGood;
+    __shared__ int sh_hcount, sh_hnext;
+    __shared__ int sh_heavy[WVA_WROW_LIST];            // (r - r_lo) * B + (b - 1) of the candidates that need the exact chain
+    __shared__ unsigned long long sh_key;
+    __shared__ unsigned long long sh_cnt[3];
+
+    const int pairSlice = blockIdx.x / gp.n_rchunks;
+    const int pairLocal = gp.pair_base + pairSlice;
+    const int rchunk = blockIdx.x % gp.n_rchunks;
+    const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
+    const int s = gp.s0 + sl;
+    const int r_lo = rchunk * gp.r_chunk + 1;
+    const int r_hi = min(gp.r_max, r_lo + gp.r_chunk - 1);
+    const int B = gp.b_max;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        sh_item = 0; sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
+        sh_hcount = 0; sh_hnext = 0;
+        gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
+    }
+    const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
+    GridServer gs;
+    int blockStatus = WVA_CAND_OK;
+    if (!pairOk) blockStatus = WVA_CAND_ERR_PAIR;
+    else {
+        load_grid_server(sys, s, a, gs);
+        if (gs.inTok < 0 || gs.outTok < 1 || gs.sloTTFT < 0.0f || gs.sloITL < 0.0f || gs.sloTPS < 0.0f)
+            blockStatus = WVA_CAND_ERR_CONFIG;
+    }
+    const size_t candBase = ((size_t)pairLocal * gp.r_max) * (size_t)B;
+    if (blockStatus != WVA_CAND_OK) {
+        if (gp.status || gp.cube) {
+            const size_t n = (size_t)(r_hi - r_lo + 1) * B;
+            const size_t off = candBase + (size_t)(r_lo - 1) * B;
+            for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+                if (gp.status) gp.status[off + i] = (unsigned char)blockStatus;
+                if (gp.cube) { float4 z = make_float4(0, 0, 0, 0); float4* c = reinterpret_cast<float4*>(&gp.cube[off + i]); c[0] = z; c[1] = z; }
+            }
+        }
+        return;
+    }
+    __syncthreads();
+    ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
+    double2* gtab = (rchunk == 0) ? gp.pair_tab + (size_t)pairSlice * B : nullptr;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        float r = sf.rate(i + 1);
+        rateF[i] = r;
+        double d = (double)r;
+        double y = rcp_refined(d);
+        rateD[i] = d; rcp[i] = y;
+        if (gtab) gtab[i] = make_double2(d, y);
+        if (!(r > 0.0f) || !(r < CUDART_INF_F)) atomicMin(&sh_nGood, i);
+    }
+    const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
+    __syncthreads();
+    ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
+    const int nGood = sh_nGood;
+
+    const int nRows = r_hi - r_lo + 1;
+    unsigned long long bestKey = WVA_KEY_NONE;
+    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    unsigned long long steps = 0, algSteps = 0, okCount = 0;
+    for (;;) {
+        int item;
+        if (lane == 0) item = atomicAdd(&sh_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nRows) break;
+        const int r = r_lo + item;
+        const float rate = gs.totalRate / (float)r;
+        const float lambda = rate / 1000.0f;
+        double lam = (double)lambda;
+        const bool lamOk = (lam >= 0x1p-100 && lam <= 0x1p20);
+        lam = pin(lam);
+        const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
+        value = value + 0.0f;
+        // shared ramp state (identical in all lanes)
+        double p = 1.0, sum = 1.0, uN = 0.0, dn = 0.0;
+        double exInSys = 0.0, exSumP = 0.0;     // exact normalised sums of a stopped row
+        unsigned thrHi = 0u, hmin = 0x3ff00000u;
+        bool stopped = false;        // ramp died out: sums frozen
+        bool broken = !lamOk;        // chain left the value window (or bad table entry)
+        const size_t rowBase = candBase + (size_t)(r - 1) * B;
+        for (int n0 = 0; n0 < B; n0 += 32) {
+            // ---- 32 steps of the shared ramp; lane l keeps the state after step n0 + l ----
+            double cP = 1.0, cSum = 1.0, cUN = 0.0;
+            bool cStopped = false, cBroken = true;
+            const int nEnd = (n0 + 32 < B) ? n0 + 32 : B;
+            for (int n = n0; n < nEnd; ++n) {
+                // four steps at once while nothing special can happen in them (see ramp_run): all quotients
+                // inside the division window and none below the die-out threshold
+                if (!stopped && !broken && n > 0 && n + 4 <= nEnd && n + 4 <= nGood) {
+                    const double p1 = div_core(p * lam, rateD[n], rcp[n]);
+                    const double p2 = div_core(p1 * lam, rateD[n + 1], rcp[n + 1]);
+                    const double p3 = div_core(p2 * lam, rateD[n + 2], rcp[n + 2]);
+                    const double p4 = div_core(p3 * lam, rateD[n + 3], rcp[n + 3]);
+                    const unsigned h1 = (unsigned)__double2hiint(p1), h2 = (unsigned)__double2hiint(p2);
+                    const unsigned h3 = (unsigned)__double2hiint(p3), h4 = (unsigned)__double2hiint(p4);
+                    const unsigned wmax = max(max(h1 - WVA_WIN_LO, h2 - WVA_WIN_LO), max(h3 - WVA_WIN_LO, h4 - WVA_WIN_LO));
+                    const unsigned hm = min(min(h1, h2), min(h3, h4));
+                    if (wmax < WVA_WIN_SPAN && !(hm < thrHi && tame)) {
+                        const double s1 = sum + p1, s2 = s1 + p2, s3 = s2 + p3, s4 = s3 + p4;
+                        const double d1 = dn + 1.0, d2 = d1 + 1.0, d3 = d2 + 1.0, d4 = d3 + 1.0;
+                        const double u1 = uN + d1 * p1, u2 = u1 + d2 * p2, u3 = u2 + d3 * p3, u4 = u3 + d4 * p4;
+                        const int k = lane - (n - n0);
+                        if ((unsigned)k < 4u) {
+                            cP = k == 0 ? p1 : (k == 1 ? p2 : (k == 2 ? p3 : p4));
+                            cSum = k == 0 ? s1 : (k == 1 ? s2 : (k == 2 ? s3 : s4));
+                            cUN = k == 0 ? u1 : (k == 1 ? u2 : (k == 2 ? u3 : u4));
+                            cStopped = false; cBroken = false;
+                        }
+                        p = p4; sum = s4; dn = d4; uN = u4;
+                        hmin = hm < hmin ? hm : hmin;
+                        if (lane == 0) steps += 4;
+                        n += 3;
+                        continue;
+                    }
+                }
+                const int b = n + 1;
+                if (!stopped && !broken) {
+                    if (b > nGood) broken = true;
+                    else {
+                        const double t = p * lam;
+                        const double pn = div_core(t, rateD[n], rcp[n]);
+                        const unsigned hq = (unsigned)__double2hiint(pn);
+                        if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) broken = true;
+                        else {
+                            sum += pn; dn += 1.0; uN += dn * pn; p = pn;
+                            if (lane == 0) ++steps;
+                            if (n == 0 && pn >= 0x1p-400)
+                                thrHi = (unsigned)__double2hiint((0x1p-68 * fmin(1.0, pn)) / (double)(11 * B));
+                            hmin = hq < hmin ? hq : hmin;
+                            if (hq < thrHi && tame && lambda <= 0.998f * rateF[n] && sum <= 0x1p400) {
+                                // the chain has died out: one exact second pass for the rest of the row (see k_grid_rows)
+                                stopped = true;
+                                const double S = sum;
+                                if ((int)(hmin >> 20) - (int)((unsigned)__double2hiint(S) >> 20) < -1000) broken = true;
+                                else {
+                                    const double yS = rcp_refined(S);
+                                    double q = div_core(1.0, S, yS), pp = 1.0, di = 0.0;
+                                    exSumP = q; exInSys = 0.0;
+                                    for (int i = 1; i <= b; ++i) {
+                                        pp = div_core(pp * lam, rateD[i - 1], rcp[i - 1]);
+                                        q = div_core(pp, S, yS);
+                                        di += 1.0;
+                                        exInSys += di * q;
+                                        exSumP += q;
+                                    }
+                                    if (lane == 0) steps += (unsigned long long)b;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (n - n0 == lane) { cP = p; cSum = sum; cUN = uN; cStopped = stopped; cBroken = broken; }
+            }
+            // ---- the 32 candidates (r, n0 + lane + 1) ----
+            const int n = n0 + lane;
+            if (n >= B) continue;
+            const int b = n + 1;
+            const size_t ci = rowBase + (size_t)n;
+            const int K = 11 * b;
+            const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
+            const float rateMax = lambdaMax * 1000.0f;
+            int st;
+            bool feasible = false;
+            wva_metrics m;
+            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            if (b > nGood) {                                   // bad table entry: literal path decides
+                int k = atomicAdd(gp.slow_count, 1);
+                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+                continue;
+            }
+            if (rate <= 0.0f) st = WVA_CAND_ERR_RATE_LE0;
+            else if (rate > rateMax) st = WVA_CAND_ERR_RATE_MAX;
+            else if (lambda < 0.0f) st = WVA_CAND_ERR_MODEL;
+            else {
+                SolveStats so;
+                bool certified = false;
+                if (!cBroken) {
+                    if (cStopped) {
+                        const double inServ = exInSys + (1.0 - exSumP) * (double)b;
+                        finish_stats(so, lambda, inServ, exInSys, 0.0f);
+                        certified = true;
+                    } else {
+                        CertIn c; c.pN = cP; c.sumRamp = cSum; c.uN = cUN; c.lam = lam; c.sTail = rateD[n]; c.N = b; c.K = K; c.lambda = lambda;
+                        certified = cert_eval(c, so);
+                    }
+                }
+                if (!certified) {
+                    // the exact chain: later, by all warps of the block (inline only when the list is full)
+                    // the exact chain: in the deferred-chain kernel (one warp per chain, all SMs); only when that
+                    // list is full, in this block's own list below
+                    {
+                        int k = atomicAdd(gp.heavy_count, 1);
+                        if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)ci; gp.heavy_cost[k] = (float)K; continue; }
+                    }
+                    const int hk = atomicAdd(&sh_hcount, 1);
+                    if (hk < WVA_WROW_LIST) { sh_heavy[hk] = (r - r_lo) * B + n; continue; }
+                    float rt, dc;
+                    int st2 = analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
+                    if (st2 < 0) { int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)ci; continue; }
+                    so.avgServTime = 0.0f;      // metrics already final in m
+                    st = st2;
+                    goto have_metrics;
+                }
+                st = WVA_CAND_OK;
+                {
+                    const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+                    float rho = so.avgNumInServers / (float)b;
+                    rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+                    m.throughput = so.throughput * 1000.0f;
+                    m.avg_resp_time = so.avgRespTime;
+                    m.avg_wait_time = so.avgWaitTime;
+                    m.avg_num_in_serv = so.avgNumInServers;
+                    m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
+                    m.avg_token_time = decode_time(gs.sp, effConc);
+                    m.max_rate = rateMax;
+                    m.rho = rho;
+                }
+            have_metrics:
+                if (st != WVA_CAND_OK) {
+                    m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                    m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+                    goto write_out;
+                }
+                okCount++;
+                algSteps += 2ULL * (unsigned long long)(K + 1);
+                const float lamMaxBack = rateMax / 1000.0f;
+                const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+                const float ttft = m.avg_wait_time + m.avg_prefill_time;
+                const float itl = m.avg_token_time;
+                feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
+                           (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && (r >= gs.minReplicas);
+                if (feasible && value == value) {              // a NaN value is never selected
+                    const unsigned long long key = make_key(value, a, r, b);
+                    if (key < bestKey) { bestKey = key; bestItl = itl; bestTtft = ttft; bestRho = m.rho; }
+                }
+            }
+        write_out:
+            if (gp.cube) {
+                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+            }
+            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+        }
+    }
+
+    // ---- the block's uncertified candidates: exact chains, one per WARP (warp_exact) --------------
+    __syncthreads();
+    {
+        const int nHeavy = sh_hcount < WVA_WROW_LIST ? sh_hcount : WVA_WROW_LIST;
+        double* wx = reinterpret_cast<double*>(smem_raw + (((size_t)B * 20 + 15) & ~(size_t)15)) +
+                     (size_t)(threadIdx.x >> 5) * (WVA_WX_CP + 1 + 1024);
+        for (;;) {
+            int idx;
+            if (lane == 0) idx = atomicAdd(&sh_hnext, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= nHeavy) break;
+            const int code = sh_heavy[idx];
+            const int r = r_lo + code / B, n = code % B, b = n + 1;
+            const size_t ci = candBase + (size_t)(r - 1) * B + (size_t)n;
+            const float rate = gs.totalRate / (float)r;
+            const float lambda = rate / 1000.0f;
+            wva_metrics m;
+            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            float rateTPS = 0.0f, dc = 0.0f;
+            bool feasible = false;
+            int st = WVA_CAND_OK;
+            SolveStats so;
+            unsigned long long wsteps = 0;
+            if (warp_exact(tb, b, 11 * b, lambda, wx, wx + WVA_WX_CP + 1, lane, so, wsteps)) {
+                // same epilogue as analyze_table
+                const float rateMax = (rateF[n] * (1.0f - WVA_EPSILON)) * 1000.0f;
+                const float lamMaxBack = rateMax / 1000.0f;
+                rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+                const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+                float rho = so.avgNumInServers / (float)b;
+                rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+                m.throughput = so.throughput * 1000.0f;
+                m.avg_resp_time = so.avgRespTime;
+                m.avg_wait_time = so.avgWaitTime;
+                m.avg_num_in_serv = so.avgNumInServers;
+                m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
+                m.avg_token_time = decode_time(gs.sp, effConc);
+                m.max_rate = rateMax;
+                m.rho = rho;
+                steps += wsteps;
+            } else if (lane == 0) {
+                st = analyze_table(tb, gs, b, rate, tame, 0, m, rateTPS, steps, dc);     // per-thread solver, all cases
+            }
+            __syncwarp();
+            if (lane != 0) continue;
+            if (st < 0) { int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)ci; continue; }
+            if (st == WVA_CAND_OK) {
+                okCount++;
+                algSteps += 2ULL * (unsigned long long)(11 * b + 1);
+                const unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
+                if (key < bestKey) {
+                    bestKey = key; bestItl = m.avg_token_time; bestTtft = m.avg_wait_time + m.avg_prefill_time; bestRho = m.rho;
+                }
+            } else {
+                m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            }
+            if (gp.cube) {
+                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+            }
+            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+        }
+    }
+
+    // ---- warp-shuffle then block argmin; the owner of the block minimum publishes its metrics ----
+    unsigned long long warpKey = bestKey;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
+        if (other < warpKey) warpKey = other;
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
+        okCount += __shfl_down_sync(0xffffffffu, okCount, o);
+    }
+    if (lane == 0) {
+        if (warpKey != WVA_KEY_NONE) atomicMin(&sh_key, warpKey);
+        atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
+    }
+    __syncthreads();
+    const unsigned long long blockKey = sh_key;
+    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {
+        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
+        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
+        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        gp.block_slot[blockIdx.x] = sl_;
+        atomicMin(&gp.keys[sl], blockKey);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
+    }
+}
+
 // Candidate evaluated through the formula-based analyzer.  Same arithmetic as analyze_table, hence
 // the same bits.  tab: the pair's published {rate, reciprocal} table (unified-loop streaming solver)
 // or nullptr; scratch: p[] for the literal path or nullptr.
@@ -1201,6 +1569,114 @@ k_grid_list(DevSystem sys, GridParams gp, const unsigned long long* __restrict__
         okc += __shfl_down_sync(0xffffffffu, okc, o);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd(&gp.counters[0], steps);
+        if (alg) atomicAdd(&gp.counters[1], alg);
+        if (okc) atomicAdd(&gp.counters[2], okc);
+    }
+}
+
+// Deferred candidates, one WARP each (warp_exact): for short lists, where the latency of a single
+// exact chain -- not throughput -- sets the duration of the phase.  The warp copies the first b
+// entries of the pair's published table into its shared-memory slice, runs the cooperative exact
+// chain and lane 0 publishes like k_grid_list; chains outside warp_exact's scope fall back to the
+// per-thread analyzer on lane 0.  Dynamic shared memory: per warp 2 b_max + WVA_WX_CP + 1 + 1024 doubles.
+#define WVA_LISTW_WARPS 4
+__global__ void __launch_bounds__(WVA_LISTW_WARPS * 32)
+k_grid_list_warp(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, int nList, int slot_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int B = gp.b_max;
+    double* rateD = reinterpret_cast<double*>(smem_raw) + (size_t)w * (2 * (size_t)B + WVA_WX_CP + 1 + 1024);
+    double* rcp = rateD + B;
+    double* cp = rcp + B;
+    double* qbuf = cp + WVA_WX_CP + 1;
+    unsigned long long steps = 0, alg = 0, okc = 0;
+    for (int t = blockIdx.x * WVA_LISTW_WARPS + w; t < nList; t += gridDim.x * WVA_LISTW_WARPS) {
+        const size_t ci = (size_t)list[t];
+        const int b = (int)(ci % B) + 1;
+        const int r = (int)((ci / B) % gp.r_max) + 1;
+        const int pairLocal = (int)(ci / ((size_t)B * gp.r_max));
+        const int sl = pairLocal / sys.A, a = pairLocal % sys.A, s = gp.s0 + sl;
+        const double2* tab = gp.pair_tab + (size_t)(pairLocal - gp.pair_base) * B;
+        __syncwarp();
+        for (int i = lane; i < b; i += 32) { const double2 v = tab[i]; rateD[i] = v.x; rcp[i] = v.y; }
+        __syncwarp();
+        GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0;
+        m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+        m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+        GridSlot slot; slot.key = WVA_KEY_NONE; slot.cost = slot.itl = slot.ttft = slot.rho = 0.0f; slot.sl = sl; slot.pad = 0;
+        load_grid_server(sys, s, a, gs);
+        rate = gs.totalRate / (float)r;
+        const float lambda = rate / 1000.0f;
+        const float rateMax = ((float)rateD[b - 1] * (1.0f - WVA_EPSILON)) * 1000.0f;
+        int st;
+        ServTable tb; tb.rateF = nullptr; tb.rateD = rateD; tb.rcp = rcp;
+        SolveStats so;
+        unsigned long long wsteps = 0;
+        const bool inScope = rate > 0.0f && !(rate > rateMax) && !(lambda < 0.0f);
+#ifdef WVA_DEBUG_CAREFUL
+        const long long tdbg0 = clock64();
+        const bool wxok = inScope && warp_exact(tb, b, 11 * b, lambda, cp, qbuf, lane, so, wsteps);
+        const long long tdbg1 = clock64();
+        if (lane == 0) printf("listwarp b=%d lambda=%g rho=%g ok=%d cycles=%lld\n", b, (double)lambda, (double)lambda / rateD[b - 1], (int)wxok, tdbg1 - tdbg0);
+        if (wxok) {
+#else
+        if (inScope && warp_exact(tb, b, 11 * b, lambda, cp, qbuf, lane, so, wsteps)) {
+#endif
+            const float lamMaxBack = rateMax / 1000.0f;
+            rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+            const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+            float rho = so.avgNumInServers / (float)b;
+            rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+            m.throughput = so.throughput * 1000.0f;
+            m.avg_resp_time = so.avgRespTime;
+            m.avg_wait_time = so.avgWaitTime;
+            m.avg_num_in_serv = so.avgNumInServers;
+            m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
+            m.avg_token_time = decode_time(gs.sp, effConc);
+            m.max_rate = rateMax;
+            m.rho = rho;
+            st = WVA_CAND_OK;
+            if (lane == 0) steps += wsteps;
+        } else if (lane == 0) {
+#ifdef WVA_DEBUG_CAREFUL
+            const long long tf0 = clock64();
+#endif
+            st = analyze_candidate(sys, s, a, r, b, tab, nullptr, gs, m, rate, rateTPS, fault, steps);
+#ifdef WVA_DEBUG_CAREFUL
+            printf("listwarp fallback b=%d cycles=%lld\n", b, clock64() - tf0);
+#endif
+        }
+        __syncwarp();
+        if (lane != 0) continue;
+        if (fault == 1) {
+            int k = atomicAdd(gp.slow_count, 1);
+            if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+        } else {
+            bool feasible = false;
+            if (st == WVA_CAND_OK) {
+                unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
+                if (key != WVA_KEY_NONE) {
+                    slot.key = key; slot.itl = m.avg_token_time; slot.ttft = m.avg_wait_time + m.avg_prefill_time;
+                    slot.rho = m.rho; slot.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+                    if (key < gp.keys[sl]) atomicMin(&gp.keys[sl], key);
+                }
+                alg += 2ULL * (unsigned long long)(11 * b + 1);
+                okc += 1;
+            } else {
+                m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            }
+            if (gp.cube) {
+                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+            }
+            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+        }
+        gp.list_slot[slot_base + t] = slot;
+    }
+    if (lane == 0) {
         if (steps) atomicAdd(&gp.counters[0], steps);
         if (alg) atomicAdd(&gp.counters[1], alg);
         if (okc) atomicAdd(&gp.counters[2], okc);

@@ -81,6 +81,10 @@ def test_config2_full_sweep_properties(wva, oracle, ctx):
     ctx.set_certified_tails(5)          # certified tails, one thread per row (shared ramp)
     ctx.upload(img)
     best_z, cube_z, status_z = ctx.analyze_grid(R, B, want_cube=True)
+    ctx.set_certified_tails(9)          # certified tails, one warp per row (lanes = batch sizes)
+    ctx.upload(img)
+    best_w, cube_w, status_w = ctx.analyze_grid(R, B, want_cube=True)
+    assert best_w.tobytes() == best.tobytes() and cube_w.tobytes() == cube.tobytes() and np.array_equal(status_w, status)
     ctx.set_certified_tails(True)
     ctx.upload(img)
     assert best_x.tobytes() == best.tobytes() and cube_x.tobytes() == cube.tobytes() and np.array_equal(status_x, status)

@@ -139,7 +139,7 @@ def test_pairs_overflow_rescale_path(wva, oracle, ctx):
     assert wfe.sum() >= 6
 
 
-@pytest.mark.parametrize("mode", [1, 0, 3, 5])      # auto / exact chains only / certified per candidate / certified per row
+@pytest.mark.parametrize("mode", [1, 0, 3, 5, 9])   # auto / exact chains only / certified per candidate / thread per row / warp per row
 @pytest.mark.parametrize("seed,S,A,R,B", [(31, 6, 3, 8, 48), (32, 3, 2, 5, 70), (33, 2, 1, 64, 33), (35, 4, 2, 6, 130)])
 def test_grid_matches_oracle(wva, oracle, ctx, seed, S, A, R, B, mode):
     img = wva.synth.make_system(S, A, seed=seed, zero_load_fraction=0.0)

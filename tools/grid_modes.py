@@ -10,7 +10,7 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 img, c = wva.synth.baseline_config(cfg)
 ctx = binding.Context(0)
 ctx.upload(img)
-for mode, name in ((3, "per candidate"), (5, "per row"), (1, "auto")):
+for mode, name in ((3, "per candidate"), (5, "thread per row"), (9, "warp per row"), (1, "auto")):
     ctx.set_certified_tails(mode)
     ts = []
     for i in range(4):
