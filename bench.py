@@ -46,6 +46,24 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
+def ncu_traffic(kernel, cfg_id):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` summary
+    of the same workload (profiles/ncu_full_r01_cfg<k>.json), per launch; None when there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_full_r01_cfg%d.json" % cfg_id)
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        for k in json.load(open(p)):
+            if k["kernel"].split("(")[0] == kernel:
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = k[key].split()
+                    tot += float(v.replace(",", "")) * mult[u]
+                return tot
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -347,7 +365,7 @@ def main():
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": ("k_grid_rows" if rows_mode else "k_grid") + " (+ k_grid_list for uncertified chains)", "kernel_us": k_us,
+                         "traffic": ncu_traffic("k_grid_rows" if rows_mode else "k_grid", args.config) if want_cube else None, "peak_source": peak_src, "kernel": ("k_grid_rows" if rows_mode else "k_grid") + " (+ k_grid_list for uncertified chains)", "kernel_us": k_us,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the sweep is FP64/issue bound, not HBM bound (see fp64); HBM fraction reported because BASELINE.json asks for it"},
             "fp64": {"chain_steps_executed": counters["steps_executed"], "chain_steps_reference": counters["steps_algorithmic"],
