@@ -267,7 +267,7 @@ def main():
         """hot path with the image resident in HBM; decisions stay in HBM."""
         ctx.analyze(R, B, want_cube=want_cube)       # Server.Calculate for all pairs || candidate sweep
         solve_step(False)
-        ctx.allocate_by_type()
+        ctx.allocate_by_type(download=False)
         allreduce_totals()
 
     def step_e2e():

@@ -283,7 +283,9 @@ int wva_solve_stats(wva_ctx* ctx, uint64_t out[4]);
 /* Replaces System.AllocateByType (pkg/core/system.go:271-300): per accelerator type
  * count += replicas*numInstances*multiplicity, cost += alloc.cost over this rank's shard.
  * The sums are left in a device buffer (wva_type_totals_device) so the host can run the
- * one NCCL allreduce of the path on it in place; this call returns the LOCAL totals. */
+ * exchange step of the path on it; this call returns the LOCAL totals.  With count == cost == NULL
+ * nothing is copied back and the call does not wait for the device (same for wva_solve in unlimited
+ * mode with chosen_acc == chosen == NULL): later calls are ordered on the context's stream. */
 int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost);
 
 /* Device address of the {int64 count[T]; then float cost[T]} totals written by the last

@@ -249,7 +249,10 @@ class Context:
         self._ck(lib().wva_solve(self._h, C.byref(spec), abi.ptr(chosen_acc, C.c_int32), C.byref(chosen.c)))
         return chosen_acc, chosen
 
-    def allocate_by_type(self):
+    def allocate_by_type(self, download=True):
+        if not download:           # totals stay on the device (type_totals_device)
+            self._ck(lib().wva_allocate_by_type(self._h, None, None))
+            return None
         count = np.zeros(self.image.T, dtype=np.int64)
         cost = np.zeros(self.image.T, dtype=np.float32)
         self._ck(lib().wva_allocate_by_type(self._h, abi.ptr(count, C.c_int64), abi.ptr(cost, C.c_float)))

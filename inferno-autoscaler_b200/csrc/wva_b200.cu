@@ -5,7 +5,9 @@
 #include "wva_kernels.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -94,6 +96,9 @@ struct SweepWorker {
 struct wva_ctx {
     int device = 0;
     SweepWorker worker;
+    // wva_analyze: the calling thread does not enter its first stream synchronisation before the sweep thread
+    // has issued its kernel (a thread blocked in a synchronisation call can hold up the other's launches)
+    std::atomic<bool> sweep_launched{true};
     // host-side plan of the per-pair service-rate tables of k_pairs_warp: an upper bound of every pair's
     // N from the uploaded image (pair_batch_size without the validity tests), offsets for the shard
     std::vector<long long> hostN;
@@ -144,6 +149,10 @@ struct wva_ctx {
     DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch;
     int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
+    // solve / totals phases: own event pairs, read lazily (a call that returns nothing to the host does not
+    // wait for the device; wva_phase_time_usec does)
+    cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT0 = nullptr, evT1 = nullptr;
+    mutable bool pendS = false, pendT = false;
     int grid_r = 0, grid_b = 0; bool grid_valid = false;
     uint64_t grid_counters[3] = {0, 0, 0};
 
@@ -248,6 +257,8 @@ int wva_ctx_create(int device, wva_ctx** out) {
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evh0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evh1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->evS0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evS1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->evT0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evT1)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evg0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evg1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
@@ -255,6 +266,16 @@ int wva_ctx_create(int device, wva_ctx** out) {
         std::string msg = std::string("stream/event create: ") + cudaGetErrorString(e);
         delete ctx;
         return fail(nullptr, WVA_ECUDA, msg);
+    }
+    // The pair kernel and the sweep run side by side on two streams.  They ask for different amounts of shared
+    // memory; with the default (per-kernel) L1/shared split an SM has to drain before it can take blocks of the
+    // other kernel, and the two were observed to run one after the other every other step.  One split for all.
+    {
+        const void* kernels[] = {(const void*)k_grid, (const void*)k_grid_rows, (const void*)k_grid_wrow, (const void*)k_grid_list,
+                                 (const void*)k_grid_list_warp, (const void*)k_pairs_warp, (const void*)k_pairs, (const void*)k_grid_claim,
+                                 (const void*)k_grid_best_init};
+        for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
     }
     *out = ctx;
     return WVA_OK;
@@ -279,6 +300,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaEventDestroy(ctx->evk1);
     cudaEventDestroy(ctx->evh0);
     cudaEventDestroy(ctx->evh1);
+    cudaEventDestroy(ctx->evS0); cudaEventDestroy(ctx->evS1); cudaEventDestroy(ctx->evT0); cudaEventDestroy(ctx->evT1);
     cudaEventDestroy(ctx->evg0);
     cudaEventDestroy(ctx->evg1);
     cudaEventDestroy(ctx->evJoin);
@@ -290,8 +312,21 @@ void wva_ctx_destroy(wva_ctx* ctx) {
 
 void* wva_stream(const wva_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t wva_launch_count(const wva_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
-int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase) { return (ctx && phase >= 0 && phase < 8) ? ctx->phase_usec[phase] : 0; }
-int64_t wva_solution_time_usec(const wva_ctx* ctx) { return ctx ? ctx->phase_usec[WVA_PHASE_SOLVE] : 0; }
+static void resolve_lazy_timers(const wva_ctx* ctx) {
+    wva_ctx* c = const_cast<wva_ctx*>(ctx);
+    float ms = 0.0f;
+    if (c->pendS && cudaEventSynchronize(c->evS1) == cudaSuccess && cudaEventElapsedTime(&ms, c->evS0, c->evS1) == cudaSuccess)
+        c->phase_usec[WVA_PHASE_SOLVE] = (int64_t)(ms * 1000.0f + 0.5f);
+    if (c->pendT && cudaEventSynchronize(c->evT1) == cudaSuccess && cudaEventElapsedTime(&ms, c->evT0, c->evT1) == cudaSuccess)
+        c->phase_usec[WVA_PHASE_TOTALS] = (int64_t)(ms * 1000.0f + 0.5f);
+    c->pendS = c->pendT = false;
+}
+int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase) {
+    if (!ctx || phase < 0 || phase >= 8) return 0;
+    resolve_lazy_timers(ctx);
+    return ctx->phase_usec[phase];
+}
+int64_t wva_solution_time_usec(const wva_ctx* ctx) { return wva_phase_time_usec(ctx, WVA_PHASE_SOLVE); }
 
 // ---------------------------------------------------------------------------------------------
 int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
@@ -471,6 +506,7 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
         LAUNCH_CHECK();
         }
         CK(cudaMemcpyAsync(&slow, ctx->slowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        while (!ctx->sweep_launched.load(std::memory_order_acquire)) std::this_thread::yield();
         CK(cudaStreamSynchronize(ctx->stream));
     }
     if (slow > 0) {
@@ -727,6 +763,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);
             else k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
+            ctx->sweep_launched.store(true, std::memory_order_release);
             CK(cudaEventRecord(ctx->evk1, ctx->gstream));
             CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->gstream));
             CK(cudaStreamSynchronize(ctx->gstream));
@@ -849,9 +886,25 @@ int wva_analyze(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube) {
     int rcGrid = WVA_OK;
     const int dev = ctx->device;
     if (!ctx->worker.th.joinable()) ctx->worker.start();
-    ctx->worker.submit([&] { cudaSetDevice(dev); rcGrid = grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0, false); });
+    static const bool timeline = std::getenv("WVA_TIMELINE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    double tg0 = 0, tg1 = 0;
+    ctx->sweep_launched.store(false, std::memory_order_release);
+    ctx->worker.submit([&] {
+        tg0 = now(); cudaSetDevice(dev);
+        rcGrid = grid_run(ctx, r_max, b_max, want_cube != 0, want_cube != 0, false);
+        ctx->sweep_launched.store(true, std::memory_order_release);      // also on the error paths
+        tg1 = now();
+    });
+    const double t1 = now();
     int rcPairs = wva_analyze_pairs(ctx, nullptr, nullptr);
+    const double t2 = now();
     ctx->worker.wait();
+    const double t3 = now();
+    if (timeline)
+        fprintf(stderr, "analyze: submit %.0f us, pairs call %.0f us, wait for sweep %.0f us | sweep thread started at +%.0f, ran %.0f us\n",
+                t1 - t0, t2 - t1, t3 - t2, tg0 - t0, tg1 - tg0);
     // join: later work on the main stream sees the sweep's results
     CK(cudaEventRecord(ctx->evJoin, ctx->gstream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
@@ -909,7 +962,8 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
     CK(cudaSetDevice(ctx->device));
     const int S = ctx->S, A = ctx->A, T = ctx->T;
     CK(carve_allocs(ctx->chosenBuf, (size_t)(S ? S : 1), ctx->chosen, nullptr, &ctx->chosen_acc));
-    PhaseTimer timer(ctx, WVA_PHASE_SOLVE);
+    PhaseTimer timer(ctx, WVA_PHASE_SOLVE, ctx->stream, ctx->evS0, ctx->evS1);
+    ctx->pendS = false;
     int first = 0, count = S;
     if (spec->unlimited) {
         first = ctx->s0; count = ctx->ns;          // separable: a rank solves its own servers
@@ -1026,6 +1080,14 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
         // device copy no longer equals Server.Calculate's output
         ctx->pairs_valid = false;
     }
+    if (spec->unlimited && !chosen_acc && !chosen) {
+        // nothing goes back to the host: leave the work queued (later calls use the same stream) and read the
+        // phase time when somebody asks for it
+        CK(cudaEventRecord(ctx->evS1, ctx->stream));
+        ctx->pendS = true;
+        ctx->solved = true;
+        return WVA_OK;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     timer.stop();
     ctx->solved = true;
@@ -1057,11 +1119,17 @@ int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost) {
     CK(cudaSetDevice(ctx->device));
     const int T = ctx->T;
     CK(ctx->totals.ensure((size_t)T * 12));
-    PhaseTimer timer(ctx, WVA_PHASE_TOTALS);
+    PhaseTimer timer(ctx, WVA_PHASE_TOTALS, ctx->stream, ctx->evT0, ctx->evT1);
+    ctx->pendT = false;
     long long* dcount = ctx->totals.as<long long>();
     float* dcost = (float*)(ctx->totals.as<char>() + (size_t)T * 8);
     k_totals<<<T, 1024, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->ns, ctx->chosen_acc, ctx->chosen, dcount, dcost);
     LAUNCH_CHECK();
+    if (!count && !cost) {            // totals stay on the device (wva_type_totals_device): no wait
+        CK(cudaEventRecord(ctx->evT1, ctx->stream));
+        ctx->pendT = true;
+        return WVA_OK;
+    }
     timer.stop();
     if (count) CK(cudaMemcpyAsync(count, dcount, (size_t)T * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (cost) CK(cudaMemcpyAsync(cost, dcost, (size_t)T * 4, cudaMemcpyDeviceToHost, ctx->stream));
