@@ -274,7 +274,8 @@ int wva_ctx_create(int device, wva_ctx** out) {
         const void* kernels[] = {(const void*)k_grid, (const void*)k_grid_rows, (const void*)k_grid_wrow, (const void*)k_grid_list,
                                  (const void*)k_grid_list_warp, (const void*)k_pairs_warp, (const void*)k_pairs, (const void*)k_grid_claim,
                                  (const void*)k_grid_best_init};
-        for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (!std::getenv("WVA_NO_CARVEOUT"))
+            for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaGetLastError();
     }
     *out = ctx;
@@ -506,7 +507,8 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
         LAUNCH_CHECK();
         }
         CK(cudaMemcpyAsync(&slow, ctx->slowCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        while (!ctx->sweep_launched.load(std::memory_order_acquire)) std::this_thread::yield();
+        static const bool noSpin = std::getenv("WVA_NO_SPIN") != nullptr;
+        while (!noSpin && !ctx->sweep_launched.load(std::memory_order_acquire)) std::this_thread::yield();
         CK(cudaStreamSynchronize(ctx->stream));
     }
     if (slow > 0) {
