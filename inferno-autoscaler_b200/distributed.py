@@ -4,7 +4,7 @@ Servers shard over ranks by contiguous ranges; accelerator / perf / type tables 
 Analyze needs no communication.  Optimize has ONE exchange step:
 
   * unlimited mode: each rank solves its own servers; the per-type totals of System.AllocateByType
-    (reference pkg/core/system.go:271-300) are partial sums -> one all-reduce of {count[T], cost[T]};
+    (reference pkg/core/system.go:271-300) are partial sums -> one all-gather of {count[T], cost[T]} and a sum in rank order (TotalsExchange);
   * limited mode: the greedy assignment is sequential over ALL servers (pkg/solver/greedy.go:107-166),
     so ranks all-gather their (server, accelerator) candidate rows and every rank runs the identical
     solve; totals are again reduced from per-shard partials.
