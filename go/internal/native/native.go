@@ -179,6 +179,30 @@ func (c *Context) AllocateByType(t int) ([]int64, []float32, error) {
 	return count, cost, c.err(C.wva_allocate_by_type(c.ctx, i64p(count), f32p(cost)), "wva_allocate_by_type")
 }
 
+// Analyze runs Server.Calculate for every pair of the shard and the candidate sweep side by side
+// (wva_analyze); results stay on the device for Solve / PairsFetch / GridFetch.
+func (c *Context) Analyze(rMax, bMax int) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return c.err(C.wva_analyze(c.ctx, C.int32_t(rMax), C.int32_t(bMax), 0), "wva_analyze")
+}
+
+// SetShard restricts the following calls to servers [first, first+count) (one process per GPU).
+func (c *Context) SetShard(first, count int) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return c.err(C.wva_set_shard(c.ctx, C.int32_t(first), C.int32_t(count)), "wva_set_shard")
+}
+
+// TypeTotalsMerge sums the per-rank totals blocks that the host all-gathered (device memory,
+// rank-major, 12*T bytes each) in rank order into this context's totals buffer: the exchange step of
+// a sharded reconcile.  The collective itself belongs to the caller (NCCL / MPI binding of its choice).
+func (c *Context) TypeTotalsMerge(gatheredDev unsafe.Pointer, nRanks int) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return c.err(C.wva_type_totals_merge(c.ctx, gatheredDev, C.int32_t(nRanks)), "wva_type_totals_merge")
+}
+
 // GridBest is wva_grid_best.
 type GridBest struct {
 	Acc, Replicas, Batch       int32
