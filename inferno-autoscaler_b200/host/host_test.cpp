@@ -73,6 +73,30 @@ int main() {
         sp.Capacity.push_back({"A100", 10}); sp.Capacity.push_back({"H100", 8});
         sp.Optimizer.Unlimited = false; sp.Optimizer.SaturationPolicy = "PriorityExhaustive";
         reconcile(native, sp, "limited_greedy");
+        // Allocation.Scale / ReAllocate (allocation.go:165-207) on the two-accelerator system with keepAccelerator:
+        // Server.Calculate only sizes the current accelerator, ReAllocate looks at all of them
+        {
+            config::SystemSpec sk = sp;
+            sk.Servers[0].KeepAccelerator = true;
+            sk.Optimizer.Unlimited = true;
+            core::System system(native);
+            system.SetFromSpec(sk);
+            system.Calculate();
+            const auto sv = system.GetServer("va:default");
+            core::Allocation cur; cur.accelerator = "A100"; cur.numReplicas = 1;
+            auto sc = system.Scale(cur, "va:default");
+            auto ra = system.ReAllocate("va:default");
+            auto gone = system.Scale(cur, "nobody");
+            core::Allocation odd; odd.accelerator = "L40S";
+            auto noacc = system.Scale(odd, "va:default");
+            std::printf("{\"scenario\": \"scale_realloc\", \"candidates\": %zu, \"scale\": {\"replicas\": %lld, \"inc\": %lld, \"cost\": %.9g, \"value\": %.9g}, "
+                        "\"realloc\": {\"accelerator\": \"%s\", \"replicas\": %lld, \"cost\": %.9g}, \"nil_cases\": %d, \"candidates_after\": %zu}\n",
+                        sv->AllAllocations().size(), sc.first ? (long long)sc.first->NumReplicas() : -1LL, (long long)sc.second,
+                        sc.first ? sc.first->Cost() : 0.0f, sc.first ? sc.first->Value() : 0.0f,
+                        ra.second.c_str(), ra.first ? (long long)ra.first->NumReplicas() : -1LL, ra.first ? ra.first->Cost() : 0.0f,
+                        (int)(!gone.first && gone.second == 0) + (int)(!noacc.first && noacc.second == 0),
+                        (system.Calculate(), sv->AllAllocations().size()));
+        }
     } catch (const Error& e) {
         std::printf("{\"fatal\": {\"code\": %d, \"message\": \"%s\"}}\n", e.code, e.what());
         return 1;

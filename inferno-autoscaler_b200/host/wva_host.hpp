@@ -184,18 +184,41 @@ public:
             s_crep[i] = (int32_t)sv->spec.CurrentAlloc.NumReplicas; s_ccost[i] = sv->spec.CurrentAlloc.Cost;
             servers_[serverOrder_[i]] = sv;
         }
-        wva_system_soa h{};
-        h.n_servers = S; h.n_accels = A; h.n_models = M; h.n_types = T;
-        h.acc_cost = acc_cost.data(); h.acc_multiplicity = acc_mult.data(); h.acc_type = acc_type.data(); h.type_capacity = type_cap.data();
-        h.perf_alpha = p_alpha.data(); h.perf_beta = p_beta.data(); h.perf_gamma = p_gamma.data(); h.perf_delta = p_delta.data();
-        h.perf_max_batch = p_mb.data(); h.perf_at_tokens = p_at.data(); h.perf_acc_count = p_cnt.data(); h.perf_valid = p_valid.data();
-        h.srv_model = s_model.data(); h.srv_arrival_rpm = s_arr.data(); h.srv_in_tokens = s_in.data(); h.srv_out_tokens = s_out.data();
-        h.srv_slo_ttft = s_ttft.data(); h.srv_slo_itl = s_itl.data(); h.srv_slo_tps = s_tps.data(); h.srv_target_valid = s_tv.data();
-        h.srv_priority = s_prio.data(); h.srv_min_replicas = s_minr.data(); h.srv_max_batch = s_mb.data(); h.srv_keep_acc = s_keep.data();
-        h.srv_cur_acc = s_cacc.data(); h.srv_cur_replicas = s_crep.data(); h.srv_cur_cost = s_ccost.data();
-        native_.check(wva_system_upload(native_.get(), &h));
-        analyzed_ = false;
+        uploadImage(s_keep);
+        analyzed_ = false; created_ = false;
         return spec_.Optimizer;
+    }
+
+    // Allocation.Scale (allocation.go:165-188): a fresh CreateAllocation on the allocation's own accelerator
+    // and the change in replicas.  {nullptr, 0} where the reference returns nil (and where it would
+    // dereference the nil result of CreateAllocation).
+    std::pair<std::shared_ptr<Allocation>, int64_t> Scale(const Allocation& a, const std::string& serverName) {
+        auto sv = GetServer(serverName);
+        if (!sv) return {nullptr, 0};
+        int ai = -1;
+        for (int i = 0; i < A_; ++i) if (accNames_[i] == a.accelerator) ai = i;
+        if (ai < 0) return {nullptr, 0};
+        createAll();
+        auto al = created_alloc_[(size_t)sv->index * A_ + ai];
+        if (!al) return {nullptr, 0};
+        return {std::make_shared<Allocation>(*al), al->numReplicas - a.numReplicas};
+    }
+
+    // Allocation.ReAllocate (allocation.go:190-207): the cheapest CreateAllocation over ALL accelerators
+    // (not only the server's candidates); map order canonicalised to ascending accelerator index.
+    std::pair<std::shared_ptr<Allocation>, std::string> ReAllocate(const std::string& serverName) {
+        auto sv = GetServer(serverName);
+        if (!sv) return {nullptr, std::string()};
+        createAll();
+        float minVal = 0.0f;
+        std::shared_ptr<Allocation> best;
+        for (int a = 0; a < A_; ++a) {
+            auto al = created_alloc_[(size_t)sv->index * A_ + a];
+            if (!al) continue;
+            if (minVal == 0.0f || al->value < minVal) { minVal = al->value; best = al; }
+        }
+        if (!best) return {nullptr, std::string()};
+        return {std::make_shared<Allocation>(*best), best->accelerator};
     }
 
     const std::map<std::string, std::shared_ptr<Server>>& Servers() const { return servers_; }
@@ -227,6 +250,35 @@ public:
             }
         }
         analyzed_ = true;
+    }
+
+    // CreateAllocation(server, accelerator) for every pair, candidate or not (allocation.go:27-163): the pair
+    // kernel honours Server.GetCandidateAccelerators, so the image goes up once with keepAccelerator cleared,
+    // every pair is sized in one launch, and the real image is restored.  value = cost as CreateAllocation
+    // leaves it (:161) -- the transition penalty belongs to Server.Calculate.
+    void createAll() {
+        if (created_) return;
+        const size_t n = (size_t)S_ * A_;
+        created_alloc_.assign(n, nullptr);
+        if (n) {
+            std::vector<uint8_t> none((size_t)S_, 0);
+            uploadImage(none);
+            std::vector<int32_t> acc(n); std::vector<int64_t> rep(n), bat(n); std::vector<float> cost(n), val(n), itl(n), ttft(n), rho(n), arrv(n);
+            std::vector<uint8_t> fe(n);
+            wva_alloc_soa o{acc.data(), rep.data(), bat.data(), cost.data(), val.data(), itl.data(), ttft.data(), rho.data(), arrv.data()};
+            native_.check(wva_analyze_pairs(native_.get(), &o, fe.data()));
+            for (size_t i = 0; i < n; ++i) {
+                if (!fe[i]) continue;
+                auto al = std::make_shared<Allocation>();
+                al->accelerator = acc[i] >= 0 ? accNames_[acc[i]] : std::string();
+                al->numReplicas = rep[i]; al->batchSize = bat[i]; al->cost = cost[i]; al->value = cost[i]; al->itl = itl[i];
+                al->ttft = ttft[i]; al->rho = rho[i]; al->maxArrvRatePerReplica = arrv[i];
+                created_alloc_[i] = al;
+            }
+            uploadImage(s_keep);
+            analyzed_ = false;
+        }
+        created_ = true;
     }
 
     // Solver.Solve dispatch used by solver::Solver
@@ -276,6 +328,18 @@ public:
     NativeContext& native() { return native_; }
 
 private:
+    void uploadImage(const std::vector<uint8_t>& keep) {
+        wva_system_soa h{};
+        h.n_servers = S_; h.n_accels = A_; h.n_models = M_; h.n_types = T_;
+        h.acc_cost = acc_cost.data(); h.acc_multiplicity = acc_mult.data(); h.acc_type = acc_type.data(); h.type_capacity = type_cap.data();
+        h.perf_alpha = p_alpha.data(); h.perf_beta = p_beta.data(); h.perf_gamma = p_gamma.data(); h.perf_delta = p_delta.data();
+        h.perf_max_batch = p_mb.data(); h.perf_at_tokens = p_at.data(); h.perf_acc_count = p_cnt.data(); h.perf_valid = p_valid.data();
+        h.srv_model = s_model.data(); h.srv_arrival_rpm = s_arr.data(); h.srv_in_tokens = s_in.data(); h.srv_out_tokens = s_out.data();
+        h.srv_slo_ttft = s_ttft.data(); h.srv_slo_itl = s_itl.data(); h.srv_slo_tps = s_tps.data(); h.srv_target_valid = s_tv.data();
+        h.srv_priority = s_prio.data(); h.srv_min_replicas = s_minr.data(); h.srv_max_batch = s_mb.data(); h.srv_keep_acc = keep.data();
+        h.srv_cur_acc = s_cacc.data(); h.srv_cur_replicas = s_crep.data(); h.srv_cur_cost = s_ccost.data();
+        native_.check(wva_system_upload(native_.get(), &h));
+    }
     NativeContext& native_;
     config::SystemSpec spec_;
     std::vector<std::string> accNames_, typeNames_, modelNames_, serverOrder_;
@@ -283,7 +347,8 @@ private:
     std::map<std::string, int64_t> capacity_;
     std::map<std::string, AllocationByType> allocationByType_;
     int S_ = 0, A_ = 0, M_ = 0, T_ = 0;
-    bool analyzed_ = false;
+    bool analyzed_ = false, created_ = false;
+    std::vector<std::shared_ptr<Allocation>> created_alloc_;
     std::vector<float> acc_cost, p_alpha, p_beta, p_gamma, p_delta, s_arr, s_ttft, s_itl, s_tps, s_ccost;
     std::vector<int32_t> acc_mult, acc_type, p_mb, p_at, p_cnt, s_model, s_in, s_out, s_prio, s_minr, s_mb, s_cacc, s_crep;
     std::vector<int64_t> type_cap;

@@ -61,3 +61,19 @@ def test_reconcile_sequence_through_cpp_host(wva, oracle):
     assert r["limited_greedy"]["analyze_allocations"] == int(feas.sum())
     assert lg["accelerator"] == img.acc_names[chosen.acc[0]] and lg["replicas"] == int(chosen.num_replicas[0])
     assert F(lg["cost"]) == chosen.cost[0] and F(lg["itl"]) == chosen.itl[0]
+    # Allocation.Scale / ReAllocate (allocation.go:165-207): CreateAllocation on every accelerator, candidate or
+    # not (keepAccelerator on: Server.Calculate sized the current accelerator only)
+    sr = r["scale_realloc"]
+    free = wva.SystemImage.from_spec(_spec(1200.0, 200, 80.0, 500.0, two_acc=True))
+    free.srv_keep_acc[:] = 0
+    cp, cf, _ = oracle.analyze_pairs(free)
+    a100 = free.acc_names.index("A100")
+    assert sr["candidates"] == 1 and sr["candidates_after"] == 1 and sr["nil_cases"] == 2
+    assert cf[a100] and sr["scale"]["replicas"] == int(cp.num_replicas[a100]) and sr["scale"]["inc"] == int(cp.num_replicas[a100]) - 1
+    assert F(sr["scale"]["cost"]) == cp.cost[a100] and F(sr["scale"]["value"]) == cp.cost[a100]      # value = cost (:161)
+    best, min_val = None, F(0)
+    for a in range(free.A):                      # allocation.go:193-201, map order -> ascending index
+        if cf[a] and (min_val == 0 or cp.cost[a] < min_val):
+            min_val, best = cp.cost[a], a
+    assert sr["realloc"]["accelerator"] == free.acc_names[best] and sr["realloc"]["replicas"] == int(cp.num_replicas[best])
+    assert F(sr["realloc"]["cost"]) == cp.cost[best]
