@@ -97,6 +97,27 @@ int main() {
                         (int)(!gone.first && gone.second == 0) + (int)(!noacc.first && noacc.second == 0),
                         (system.Calculate(), sv->AllAllocations().size()));
         }
+        // incremental updates (system.go:99-171): add a second server, re-optimize, remove it again
+        {
+            core::System system(native);
+            const config::OptimizerSpec& os = system.SetFromSpec(optimizerFixture(1200.0f, 200, 80.0f, 500.0f, "A100", 40.0f));
+            solver::Optimizer optimizer(os);
+            manager::Manager manager(system, optimizer);
+            config::ServerSpec vb = system.GetServer("va:default")->spec;
+            vb.Name = "vb:default"; vb.CurrentAlloc.Load.ArrivalRate = 600.0f;
+            system.AddServerFromSpec(vb);
+            system.Calculate(); manager.Optimize();
+            const long long n2 = (long long)system.Servers().size();
+            const long long ra2 = system.GetServer("va:default")->Allocation() ? (long long)system.GetServer("va:default")->Allocation()->NumReplicas() : -1;
+            const long long rb2 = system.GetServer("vb:default")->Allocation() ? (long long)system.GetServer("vb:default")->Allocation()->NumReplicas() : -1;
+            const bool removed = system.RemoveServer("vb:default"), again = system.RemoveServer("vb:default");
+            system.Calculate(); manager.Optimize();
+            const long long n1 = (long long)system.Servers().size();
+            const long long ra1 = system.GetServer("va:default")->Allocation() ? (long long)system.GetServer("va:default")->Allocation()->NumReplicas() : -1;
+            std::printf("{\"scenario\": \"incremental\", \"servers_after_add\": %lld, \"va_after_add\": %lld, \"vb_after_add\": %lld, "
+                        "\"removed\": %d, \"removed_again\": %d, \"servers_after_remove\": %lld, \"va_after_remove\": %lld}\n",
+                        n2, ra2, rb2, (int)removed, (int)again, n1, ra1);
+        }
     } catch (const Error& e) {
         std::printf("{\"fatal\": {\"code\": %d, \"message\": \"%s\"}}\n", e.code, e.what());
         return 1;

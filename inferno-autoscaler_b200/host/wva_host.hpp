@@ -189,6 +189,48 @@ public:
         return spec_.Optimizer;
     }
 
+    // Incremental updates (system.go:98-171).  The spec is edited and the image rebuilt and re-uploaded (one
+    // packed copy; a delta upload of the touched rows is the obvious refinement).  "replace if it already
+    // exists" and the not-found errors (returned as false) are the reference's.
+    void AddServerFromSpec(const config::ServerSpec& s) {
+        config::SystemSpec d = spec_;
+        bool found = false;
+        for (auto& e : d.Servers) if (e.Name == s.Name) { e = s; found = true; }
+        if (!found) d.Servers.push_back(s);
+        SetFromSpec(d);
+    }
+    bool RemoveServer(const std::string& name) {
+        config::SystemSpec d = spec_;
+        const size_t before = d.Servers.size();
+        for (size_t i = d.Servers.size(); i-- > 0;) if (d.Servers[i].Name == name) d.Servers.erase(d.Servers.begin() + (long)i);
+        if (d.Servers.size() == before) return false;
+        SetFromSpec(d);
+        return true;
+    }
+    void AddAcceleratorFromSpec(const config::AcceleratorSpec& a) {
+        config::SystemSpec d = spec_;
+        bool found = false;
+        for (auto& e : d.Accelerators) if (e.Name == a.Name) { e = a; found = true; }
+        if (!found) d.Accelerators.push_back(a);
+        SetFromSpec(d);
+    }
+    bool RemoveAccelerator(const std::string& name) {
+        config::SystemSpec d = spec_;
+        const size_t before = d.Accelerators.size();
+        for (size_t i = d.Accelerators.size(); i-- > 0;) if (d.Accelerators[i].Name == name) d.Accelerators.erase(d.Accelerators.begin() + (long)i);
+        if (d.Accelerators.size() == before) return false;
+        SetFromSpec(d);
+        return true;
+    }
+    void SetCountFromSpec(const config::AcceleratorCount& c) {
+        config::SystemSpec d = spec_;
+        bool found = false;
+        for (auto& e : d.Capacity) if (e.Type == c.Type) { e = c; found = true; }
+        if (!found) d.Capacity.push_back(c);
+        SetFromSpec(d);
+    }
+    void SetCapacityFromSpec(const std::vector<config::AcceleratorCount>& v) { for (const auto& c : v) SetCountFromSpec(c); }
+
     // Allocation.Scale (allocation.go:165-188): a fresh CreateAllocation on the allocation's own accelerator
     // and the change in replicas.  {nullptr, 0} where the reference returns nil (and where it would
     // dereference the nil result of CreateAllocation).

@@ -77,3 +77,16 @@ def test_reconcile_sequence_through_cpp_host(wva, oracle):
             min_val, best = cp.cost[a], a
     assert sr["realloc"]["accelerator"] == free.acc_names[best] and sr["realloc"]["replicas"] == int(cp.num_replicas[best])
     assert F(sr["realloc"]["cost"]) == cp.cost[best]
+    # incremental updates (system.go:99-171): a second server with half the load is added, sized and removed
+    inc = r["incremental"]
+    two = _spec(1200.0, 200, 80.0, 500.0)
+    vb = json.loads(json.dumps(two["serverData"]["servers"][0])); vb["name"] = "vb:default"
+    vb["currentAlloc"]["load"]["arrivalRate"] = 600.0
+    two["serverData"]["servers"].append(vb)
+    img2 = wva.SystemImage.from_spec(two)
+    p2, f2, _ = oracle.analyze_pairs(img2)
+    a2, c2 = oracle.solve(img2, p2, f2, unlimited=True)
+    assert inc["servers_after_add"] == 2 and inc["va_after_add"] == int(c2.num_replicas[0]) == 43
+    assert inc["vb_after_add"] == int(c2.num_replicas[1])
+    assert inc["removed"] == 1 and inc["removed_again"] == 0
+    assert inc["servers_after_remove"] == 1 and inc["va_after_remove"] == 43
