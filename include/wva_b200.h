@@ -229,6 +229,9 @@ int wva_pairs_fetch(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible);
  * fills its shard rows, the host all-gathers the rows over NCCL in place, then calls
  * wva_pairs_commit so that wva_solve may run the (sequential, replicated) greedy assignment. */
 int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
+/* Ordering contract: wva_pairs_commit waits for ALL work previously issued to the device by this
+ * process (cudaDeviceSynchronize), so the caller's collectives may run on any stream.  (With
+ * wva_comm_init the library gathers the rows itself and none of this is needed.) */
 int wva_pairs_commit(wva_ctx* ctx);
 /* Tuning: certified closed-form tails on/off.  Chains that would run a long
  * constant-rate tail are first evaluated from the exact ramp plus the geometric closed form and accepted
@@ -293,15 +296,60 @@ int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost);
  * fixed order (ascending server index) — Go sums in random map order (system.go:273,297). */
 int wva_type_totals_device(wva_ctx* ctx, void** dev_ptr, size_t* bytes);
 
-/* Sharded runs: the exchange step of the path.  Every rank all-gathers its 12*T-byte totals block
- * (ONE collective); this call then sums the n_ranks gathered blocks (device memory, rank-major) in
- * rank order into the totals buffer -- one launch, and unlike a ring/tree all-reduce the float32
- * cost sums come out the same on every rank and every run. */
+/* Sharded runs with a HOST-driven collective (no wva_comm_init): every rank all-gathers its 12*T-byte
+ * totals block (ONE collective); this call then sums the n_ranks gathered blocks (device memory,
+ * rank-major) in rank order into the totals buffer -- one launch, and unlike a ring/tree all-reduce the
+ * float32 cost sums come out the same on every rank and every run.
+ * Ordering contract: the merge kernel is enqueued on wva_stream(ctx); the caller's collective must
+ * have been enqueued on that same stream (or have completed) before this call. */
 int wva_type_totals_merge(wva_ctx* ctx, const void* gathered_dev, int32_t n_ranks);
 
 /* optimizer.SolutionTimeMsec (pkg/solver/optimizer.go:30-34): device+host time of the
  * last wva_solve in microseconds. */
 int64_t wva_solution_time_usec(const wva_ctx* ctx);
+
+/* ---- multi-GPU inside the library ------------------------------------------ *
+ * servers shard over the GPUs of one box, accelerator / perf / type tables are
+ * replicated, Analyze needs no communication, and Optimize has ONE exchange step whose site in the
+ * reference is System.AllocateByType (pkg/core/system.go:271-300).  NCCL is resolved at run time
+ * (dlopen of libnccl.so.2), so the library still loads on a box without it; the calls below then
+ * fail with WVA_ECUDA.
+ *
+ * (1) one process per GPU (torchrun, MPI, N Go processes): rank 0 obtains an id, the host
+ *     distributes its 128 bytes by any means, every rank attaches its ctx.  With a communicator
+ *     attached:
+ *       - wva_comm_shard gives the rank its contiguous server range [floor(S*g/G), floor(S*(g+1)/G));
+ *       - wva_allocate_by_type all-gathers the 12*T-byte {count, cost} partials (ONE ncclAllGather on
+ *         the ctx stream) and sums them in rank order: every rank returns the GLOBAL totals, bit-equal
+ *         on every rank and every run;
+ *       - wva_solve in limited mode first all-gathers the candidate records of all ranks' shards
+ *         (packed, ONE ncclAllGather of 45 B per (server, accelerator)), then runs the identical
+ *         sequential greedy on every rank;
+ *       - unlimited wva_solve stays local (separable), chosen_acc / chosen are filled for the shard. */
+#define WVA_COMM_ID_BYTES 128
+int wva_comm_unique_id(void* id_out /* WVA_COMM_ID_BYTES */);
+int wva_comm_init(wva_ctx* ctx, const void* id, int32_t rank, int32_t n_ranks);
+int wva_comm_destroy(wva_ctx* ctx);
+int wva_comm_info(const wva_ctx* ctx, int32_t* rank, int32_t* n_ranks);   /* 0 / 1 without a communicator */
+int wva_comm_shard(wva_ctx* ctx);
+
+/* (2) ONE process driving several GPUs -- the shape of the reference's caller, a single reconcile
+ *     goroutine (internal/controller/variantautoscaling_controller.go:143-166).  A group owns one ctx
+ *     per device and an ncclCommInitAll communicator; every call fans out to one host thread per
+ *     device and joins.  Host outputs have the full extent (S servers / S*A pairs) and are assembled
+ *     from the shards; totals are global. */
+typedef struct wva_group wva_group;
+int  wva_group_create(const int32_t* device_ids, int32_t n_devices, wva_group** out);
+void wva_group_destroy(wva_group* g);
+int32_t wva_group_size(const wva_group* g);
+wva_ctx* wva_group_ctx(wva_group* g, int32_t i);          /* per-device ctx (tuning, instrumentation) */
+const char* wva_group_last_error(const wva_group* g);
+int wva_group_upload(wva_group* g, const wva_system_soa* host);      /* replicate the image, shard the servers */
+int wva_group_analyze(wva_group* g, int32_t r_max, int32_t b_max, int32_t want_cube);   /* r_max = 0: pairs only */
+int wva_group_pairs_fetch(wva_group* g, wva_alloc_soa* out, uint8_t* feasible);
+int wva_group_grid_fetch(wva_group* g, wva_grid_best* best /* [S] */);
+int wva_group_solve(wva_group* g, const wva_optimizer_spec* spec, int32_t* chosen_acc, wva_alloc_soa* chosen);
+int wva_group_allocate_by_type(wva_group* g, int64_t* count, float* cost);
 
 /* ---- low-level analyzer API (pkg/analyzer public surface) ------------------ */
 
@@ -347,6 +395,10 @@ void* wva_stream(const wva_ctx* ctx);
  * sent to the materialised-p[] path. */
 int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap);
 int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal);
+/* Candidate ids (cube indices relative to the shard) the last sweep slice handed to the exact-chain
+ * kernel because their certificate was ambiguous or their tail outlasted tail_cap (at most cap are
+ * copied; *n = how many there were).  Test/diagnostic aid: parity tests re-evaluate exactly these. */
+int wva_grid_deferred_fetch(wva_ctx* ctx, uint64_t* ids, int32_t cap, int32_t* n);
 /* Work counters of the last grid sweep: chain steps actually executed and the
  * algorithmic chain steps (sum over analysable candidates of 2*(11b+1)). */
 int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic,

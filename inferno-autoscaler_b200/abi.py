@@ -20,6 +20,7 @@ POLICY_BY_NAME = {  # SaturatedAllocationPolicyEnum, reference pkg/config/config
 }
 
 ACC_NONE, ACC_UNKNOWN = -1, -2
+COMM_ID_BYTES = 128
 
 CAND_OK, CAND_FEASIBLE = 0, 1
 CAND_ERR_PAIR, CAND_ERR_CONFIG, CAND_ERR_RATE_LE0, CAND_ERR_RATE_MAX, CAND_ERR_MODEL = 2, 4, 6, 8, 10

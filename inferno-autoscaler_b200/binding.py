@@ -22,7 +22,10 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_pair_counters", "wva_pair_debug", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
+    "wva_comm_unique_id", "wva_comm_init", "wva_comm_destroy", "wva_comm_info", "wva_comm_shard",
+    "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx", "wva_group_last_error", "wva_group_upload",
+    "wva_group_analyze", "wva_group_pairs_fetch", "wva_group_grid_fetch", "wva_group_solve", "wva_group_allocate_by_type",
 ]
 
 
@@ -82,29 +85,83 @@ def lib():
         L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
         L.wva_grid_set_tail_cap.argtypes = [vp, i32]
         L.wva_grid_list_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.wva_grid_deferred_fetch.argtypes = [vp, C.POINTER(u64), i32, C.POINTER(i32)]
         L.wva_stream.argtypes = [vp]
         L.wva_stream.restype = vp
+        L.wva_comm_unique_id.argtypes = [vp]
+        L.wva_comm_init.argtypes = [vp, vp, i32, i32]
+        L.wva_comm_destroy.argtypes = [vp]
+        L.wva_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.wva_comm_shard.argtypes = [vp]
+        L.wva_group_create.argtypes = [abi.i32p, i32, C.POINTER(vp)]
+        L.wva_group_destroy.argtypes = [vp]
+        L.wva_group_destroy.restype = None
+        L.wva_group_size.argtypes = [vp]
+        L.wva_group_ctx.argtypes = [vp, i32]
+        L.wva_group_ctx.restype = vp
+        L.wva_group_last_error.argtypes = [vp]
+        L.wva_group_last_error.restype = C.c_char_p
+        L.wva_group_upload.argtypes = [vp, C.POINTER(abi.SystemSoa)]
+        L.wva_group_analyze.argtypes = [vp, i32, i32, i32]
+        L.wva_group_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
+        L.wva_group_grid_fetch.argtypes = [vp, vp]
+        L.wva_group_solve.argtypes = [vp, C.POINTER(abi.OptimizerSpec), abi.i32p, C.POINTER(abi.AllocSoa)]
+        L.wva_group_allocate_by_type.argtypes = [vp, abi.i64p, abi.f32p]
         if L.wva_abi_version() != abi.ABI_VERSION:
             raise ImportError("libwva_b200.so ABI version mismatch")
         _lib = L
     return _lib
 
 
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the host distributes it, every rank passes it to Context.comm_init)."""
+    buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+    rc = lib().wva_comm_unique_id(buf)
+    if rc != abi.OK:
+        raise WvaError(rc, lib().wva_last_error(None).decode())
+    return bytes(buf.raw)
+
+
 class Context:
     """wva_ctx: one CUDA device, one stream, one call in flight."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self._h = C.c_void_p()
-        rc = lib().wva_ctx_create(int(device), C.byref(self._h))
-        if rc != abi.OK:
-            raise WvaError(rc, lib().wva_last_error(None).decode())
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+        else:
+            rc = lib().wva_ctx_create(int(device), C.byref(self._h))
+            if rc != abi.OK:
+                raise WvaError(rc, lib().wva_last_error(None).decode())
         self.device = int(device)
         self.image = None
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             lib().wva_ctx_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
+
+    # ---- multi-rank (one process per GPU) ------------------------------------------------
+    def comm_init(self, unique_id, rank, n_ranks):
+        assert len(unique_id) == abi.COMM_ID_BYTES
+        self._ck(lib().wva_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(n_ranks)))
+
+    def comm_destroy(self):
+        self._ck(lib().wva_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, n = C.c_int32(0), C.c_int32(1)
+        self._ck(lib().wva_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def comm_shard(self):
+        """this rank's contiguous server range of the uploaded image: floor(S*g/G) boundaries"""
+        self._ck(lib().wva_comm_shard(self._h))
+        r, n = self.comm_info()
+        S = self.image.S
+        self.first = S * r // n
+        self.count = S * (r + 1) // n - self.first
 
     def __del__(self):
         try:
@@ -232,6 +289,13 @@ class Context:
         self._ck(lib().wva_grid_list_sizes(self._h, C.byref(a), C.byref(b)))
         return dict(deferred=a.value, literal=b.value)
 
+    def grid_deferred(self, cap=1 << 22):
+        """cube indices (relative to the shard) of the candidates the last sweep slice ran as exact chains."""
+        n = C.c_int32(0)
+        ids = np.zeros(cap, dtype=np.uint64)
+        self._ck(lib().wva_grid_deferred_fetch(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
+        return ids[:min(n.value, cap)].copy(), n.value
+
     def grid_counters(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         self._ck(lib().wva_grid_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -304,3 +368,76 @@ class Context:
         bad = C.c_uint64(0)
         self._ck(lib().wva_selftest_division(self._h, int(seed), int(n), int(mode), C.byref(bad)))
         return bad.value
+
+
+class Group:
+    """wva_group: ONE process driving several GPUs (the shape of the reference's single reconcile goroutine).
+    Servers shard over the devices; host outputs have the full extent; totals are global."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        self._h = C.c_void_p()
+        rc = lib().wva_group_create(abi.ptr(devs, C.c_int32), len(devs), C.byref(self._h))
+        if rc != abi.OK:
+            raise WvaError(rc, lib().wva_last_error(None).decode())
+        self.n = len(devs)
+        self.ctxs = [Context(int(devs[i]), _borrowed=lib().wva_group_ctx(self._h, i)) for i in range(self.n)]
+        self.image = None
+
+    def close(self):
+        if self._h:
+            lib().wva_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != abi.OK:
+            raise WvaError(rc, lib().wva_group_last_error(self._h).decode())
+
+    def upload(self, image: SystemImage):
+        s = image.c_struct()
+        self._ck(lib().wva_group_upload(self._h, C.byref(s)))
+        self.image = image
+        for i, c in enumerate(self.ctxs):
+            c.image = image
+            c.first = image.S * i // self.n
+            c.count = image.S * (i + 1) // self.n - c.first
+
+    def analyze(self, r_max=0, b_max=0, want_cube=False):
+        self._ck(lib().wva_group_analyze(self._h, int(r_max), int(b_max), 1 if want_cube else 0))
+
+    def pairs_fetch(self):
+        n = self.image.S * self.image.A
+        out = abi.AllocArrays(n)
+        feasible = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().wva_group_pairs_fetch(self._h, C.byref(out.c), abi.ptr(feasible, C.c_uint8)))
+        return out, feasible
+
+    def grid_fetch(self):
+        best = np.zeros(self.image.S, dtype=abi.GRID_BEST_DTYPE)
+        self._ck(lib().wva_group_grid_fetch(self._h, best.ctypes.data))
+        return best
+
+    def solve(self, unlimited=True, delayed_best_effort=False, policy=abi.POLICY_NONE, download=True):
+        spec = abi.OptimizerSpec(1 if unlimited else 0, 1 if delayed_best_effort else 0, int(policy))
+        if not download:
+            self._ck(lib().wva_group_solve(self._h, C.byref(spec), None, None))
+            return None
+        chosen_acc = np.full(self.image.S, -1, dtype=np.int32)
+        chosen = abi.AllocArrays(self.image.S)
+        self._ck(lib().wva_group_solve(self._h, C.byref(spec), abi.ptr(chosen_acc, C.c_int32), C.byref(chosen.c)))
+        return chosen_acc, chosen
+
+    def allocate_by_type(self, download=True):
+        if not download:
+            self._ck(lib().wva_group_allocate_by_type(self._h, None, None))
+            return None
+        count = np.zeros(self.image.T, dtype=np.int64)
+        cost = np.zeros(self.image.T, dtype=np.float32)
+        self._ck(lib().wva_group_allocate_by_type(self._h, abi.ptr(count, C.c_int64), abi.ptr(cost, C.c_float)))
+        return count, cost

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -54,6 +55,49 @@ struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+}  // namespace
+
+// NCCL, resolved at run time: the library has no link-time dependency on it (a box without NCCL can
+// still run single-GPU), and inside a process that already loaded a libnccl.so.2 (PyTorch's bundled
+// one) the same copy is used.  Only the handful of entry points the path needs; their C ABI has been
+// stable across NCCL 2.x.
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_unique_id { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+const NcclApi& nccl_api() {
+    std::call_once(g_nccl_once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.handle) break; }
+        if (!g_nccl.handle) { g_nccl.err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return; }
+        auto sym = [&](const char* n) { void* p = dlsym(g_nccl.handle, n); if (!p) g_nccl.err = std::string("missing NCCL symbol ") + n; return p; };
+        g_nccl.GetUniqueId = (int (*)(nccl_unique_id*))sym("ncclGetUniqueId");
+        g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_unique_id, int))sym("ncclCommInitRank");
+        g_nccl.CommInitAll = (int (*)(nccl_comm_t*, int, const int*))sym("ncclCommInitAll");
+        g_nccl.CommDestroy = (int (*)(nccl_comm_t))sym("ncclCommDestroy");
+        g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))sym("ncclAllGather");
+        g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+        g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+        g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        g_nccl.ok = g_nccl.err.empty();
+    });
+    return g_nccl;
+}
+constexpr int kNcclChar = 0;   // ncclInt8 / ncclChar
 }  // namespace
 
 // One helper thread per context: runs the candidate sweep's host side while the calling thread
@@ -147,7 +191,7 @@ struct wva_ctx {
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
     DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch;
-    int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0;
+    int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0, last_heavy_slice = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     // solve / totals phases: own event pairs, read lazily (a call that returns nothing to the host does not
     // wait for the device; wva_phase_time_usec does)
@@ -155,6 +199,10 @@ struct wva_ctx {
     mutable bool pendS = false, pendT = false;
     int grid_r = 0, grid_b = 0; bool grid_valid = false;
     uint64_t grid_counters[3] = {0, 0, 0};
+
+    // multi-rank exchange (wva_comm_init / wva_group_create)
+    nccl_comm_t comm = nullptr; int comm_rank = 0, comm_size = 1; bool comm_owned = false;
+    DevBuf commTotals, commChunk, commGather;
 
     // misc io buffers for the low-level API
     DevBuf ioA, ioB, ioC, ioD, ioE, ioF, ioG;
@@ -227,6 +275,32 @@ cudaError_t download_allocs(wva_ctx* ctx, const DevAllocs& d, size_t first, size
     return cudaSuccess;
 }
 
+// limited mode with a communicator: every rank packs the candidate records of its shard into one chunk,
+// ONE ncclAllGather moves all chunks, the other ranks' rows are scattered into place.
+int comm_gather_pairs(wva_ctx* ctx) {
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(ctx, WVA_ECUDA, "NCCL unavailable: " + nc.err);
+    const int A = ctx->A, G = ctx->comm_size;
+    const size_t capServers = ((size_t)ctx->S + G - 1) / G;
+    if ((size_t)ctx->ns > capServers)
+        return fail(ctx, WVA_EINVAL, "shard larger than ceil(S / ranks): use wva_comm_shard for the limited-capacity exchange");
+    const size_t cap = (capServers ? capServers : 1) * A;
+    const size_t chunkBytes = pair_chunk_bytes(cap);
+    CK(ctx->commChunk.ensure(chunkBytes));
+    CK(ctx->commGather.ensure(chunkBytes * G));
+    const int nPairs = ctx->ns * A;
+    k_pairs_pack<<<(nPairs + 255) / 256 + 1, 256, 0, ctx->stream>>>(ctx->pairs, ctx->feasible, ctx->s0 * A, nPairs, cap, ctx->commChunk.as<unsigned char>());
+    LAUNCH_CHECK();
+    int nrc = nc.AllGather(ctx->commChunk.p, ctx->commGather.p, chunkBytes, kNcclChar, ctx->comm, ctx->stream);
+    if (nrc != 0) return fail(ctx, WVA_ECUDA, std::string("ncclAllGather(pairs): ") + nc.GetErrorString(nrc));
+    dim3 grid((unsigned)((cap + 255) / 256 < 1024 ? (cap + 255) / 256 : 1024), (unsigned)G);
+    k_pairs_unpack<<<grid, 256, 0, ctx->stream>>>(ctx->commGather.as<unsigned char>(), chunkBytes, cap, ctx->comm_rank, (size_t)ctx->S * A,
+                                                   ctx->pairs, ctx->feasible);
+    LAUNCH_CHECK();
+    ctx->pairs_complete = true;
+    return WVA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -287,12 +361,14 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     ctx->worker.stop();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->comm_owned && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
     DevBuf* bufs[] = {&ctx->arena, &ctx->pairBuf, &ctx->pairN, &ctx->pairOrder, &ctx->pairHist, &ctx->slowList,
                       &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->pairPbuf, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
                       &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->ioA, &ctx->ioB,
-                      &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG};
+                      &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG, &ctx->commTotals, &ctx->commChunk, &ctx->commGather};
     for (DevBuf* b : bufs) b->release();
     ctx->staging.release();
     cudaEventDestroy(ctx->ev0);
@@ -567,6 +643,8 @@ int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible) {
 int wva_pairs_commit(wva_ctx* ctx) {
     if (!ctx) return WVA_EINVAL;
     if (!ctx->pairs_valid) return fail(ctx, WVA_ESTATE, "analyze_pairs has not run");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());       // the caller's collectives may have run on any stream
     ctx->pairs_complete = true;
     return WVA_OK;
 }
@@ -743,7 +821,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     }
     PhaseTimer timer(ctx, WVA_PHASE_GRID, ctx->gstream, ctx->evg0, ctx->evg1);
     ctx->phase_usec[WVA_PHASE_GRID_KERNEL] = 0; ctx->phase_usec[WVA_PHASE_GRID_HEAVY] = 0;
-    ctx->last_heavy = 0; ctx->last_slow = 0;
+    ctx->last_heavy = 0; ctx->last_slow = 0; ctx->last_heavy_slice = 0;
     CK(cudaMemsetAsync(ctx->keys.p, 0xff, (size_t)(ns ? ns : 1) * 8, ctx->gstream));
     CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * 8, ctx->gstream));
     if (ns > 0) {
@@ -818,7 +896,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             // keys only ever decrease towards the true minimum: redoing the slice is safe (the work
             // counters then count the slice twice)
         }
-        ctx->last_heavy += heavy; ctx->last_slow += slow;
+        ctx->last_heavy += heavy; ctx->last_slow += slow; ctx->last_heavy_slice = heavy;
         int listSlots = heavy;
         if (slow > 0) {
             size_t freeB = 0, totB = 0;
@@ -949,6 +1027,17 @@ int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal)
     if (literal) *literal = ctx->last_slow;
     return WVA_OK;
 }
+int wva_grid_deferred_fetch(wva_ctx* ctx, uint64_t* ids, int32_t cap, int32_t* n) {
+    if (!ctx || !n || cap < 0 || (cap > 0 && !ids)) return WVA_EINVAL;
+    if (!ctx->grid_valid) return fail(ctx, WVA_ESTATE, "no grid sweep has run");
+    *n = ctx->last_heavy_slice;
+    const int k = ctx->last_heavy_slice < cap ? ctx->last_heavy_slice : cap;
+    if (k > 0) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpy(ids, ctx->heavyList.p, (size_t)k * 8, cudaMemcpyDeviceToHost));
+    }
+    return WVA_OK;
+}
 int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* steps_algorithmic, uint64_t* candidates_ok) {
     if (!ctx) return WVA_EINVAL;
     if (steps_executed) *steps_executed = ctx->grid_counters[0];
@@ -975,8 +1064,12 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
             LAUNCH_CHECK();
         }
     } else {
+        if (!ctx->pairs_complete && ctx->comm) {
+            int rc = comm_gather_pairs(ctx);
+            if (rc != WVA_OK) return rc;
+        }
         if (!ctx->pairs_complete)
-            return fail(ctx, WVA_ESTATE, "limited-capacity solve needs the candidates of every server (gather them, then wva_pairs_commit)");
+            return fail(ctx, WVA_ESTATE, "limited-capacity solve needs the candidates of every server (wva_comm_init, or gather them and wva_pairs_commit)");
         // carve greedy buffers
         if (T > 256) return fail(ctx, WVA_EINVAL, "the device greedy solver holds at most 256 accelerator types");
         if ((unsigned long long)(S ? S : 1) * (unsigned long long)A >= (1ull << 31))
@@ -1127,6 +1220,15 @@ int wva_allocate_by_type(wva_ctx* ctx, int64_t* count, float* cost) {
     float* dcost = (float*)(ctx->totals.as<char>() + (size_t)T * 8);
     k_totals<<<T, 1024, 0, ctx->stream>>>(ctx->dsys, ctx->s0, ctx->ns, ctx->chosen_acc, ctx->chosen, dcount, dcost);
     LAUNCH_CHECK();
+    if (ctx->comm) {
+        // the one exchange step of the path: all-gather of the {count, cost} partials, summed in rank order
+        const NcclApi& nc = nccl_api();
+        CK(ctx->commTotals.ensure((size_t)ctx->comm_size * T * 12));
+        int nrc = nc.AllGather(ctx->totals.p, ctx->commTotals.p, (size_t)T * 12, kNcclChar, ctx->comm, ctx->stream);
+        if (nrc != 0) return fail(ctx, WVA_ECUDA, std::string("ncclAllGather(totals): ") + nc.GetErrorString(nrc));
+        k_totals_merge<<<(T + 63) / 64, 64, 0, ctx->stream>>>(T, ctx->comm_size, ctx->commTotals.as<unsigned char>(), dcount, dcost);
+        LAUNCH_CHECK();
+    }
     if (!count && !cost) {            // totals stay on the device (wva_type_totals_device): no wait
         CK(cudaEventRecord(ctx->evT1, ctx->stream));
         ctx->pendT = true;
@@ -1311,3 +1413,169 @@ extern "C" int wva_selftest_division(wva_ctx* ctx, uint64_t seed, uint64_t n, in
     CK(cudaStreamSynchronize(ctx->stream));
     return WVA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: communicator per ctx (one process per GPU) and device groups (one process, several GPUs)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int wva_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(nullptr, WVA_EINVAL, "id_out is NULL");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(nullptr, WVA_ECUDA, "NCCL unavailable: " + nc.err);
+    nccl_unique_id id;
+    int rc = nc.GetUniqueId(&id);
+    if (rc != 0) return fail(nullptr, WVA_ECUDA, std::string("ncclGetUniqueId: ") + nc.GetErrorString(rc));
+    std::memcpy(id_out, &id, WVA_COMM_ID_BYTES);
+    return WVA_OK;
+}
+
+int wva_comm_init(wva_ctx* ctx, const void* id, int32_t rank, int32_t n_ranks) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, WVA_EINVAL, "bad communicator arguments");
+    if (ctx->comm) return fail(ctx, WVA_ESTATE, "a communicator is already attached");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(ctx, WVA_ECUDA, "NCCL unavailable: " + nc.err);
+    CK(cudaSetDevice(ctx->device));
+    nccl_unique_id uid;
+    std::memcpy(&uid, id, WVA_COMM_ID_BYTES);
+    nccl_comm_t comm = nullptr;
+    int rc = nc.CommInitRank(&comm, n_ranks, uid, rank);
+    if (rc != 0) return fail(ctx, WVA_ECUDA, std::string("ncclCommInitRank: ") + nc.GetErrorString(rc));
+    ctx->comm = comm; ctx->comm_rank = rank; ctx->comm_size = n_ranks; ctx->comm_owned = true;
+    return WVA_OK;
+}
+
+int wva_comm_destroy(wva_ctx* ctx) {
+    if (!ctx) return WVA_EINVAL;
+    if (ctx->comm) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->comm_owned && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_size = 1; ctx->comm_owned = false;
+    return WVA_OK;
+}
+
+int wva_comm_info(const wva_ctx* ctx, int32_t* rank, int32_t* n_ranks) {
+    if (!ctx) return WVA_EINVAL;
+    if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
+    if (n_ranks) *n_ranks = ctx->comm ? ctx->comm_size : 1;
+    return WVA_OK;
+}
+
+int wva_comm_shard(wva_ctx* ctx) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    const long long S = ctx->S, g = ctx->comm ? ctx->comm_rank : 0, G = ctx->comm ? ctx->comm_size : 1;
+    const int first = (int)(S * g / G), last = (int)(S * (g + 1) / G);
+    return wva_set_shard(ctx, first, last - first);
+}
+
+}  // extern "C"
+
+struct wva_group {
+    std::vector<wva_ctx*> ctxs;
+    std::string err;
+    int S = 0, A = 0;
+    // run f(i, ctx) on one host thread per device, return the first failure
+    template <class F> int each(F f) {
+        const int n = (int)ctxs.size();
+        std::vector<int> rc((size_t)n, WVA_OK);
+        if (n == 1) rc[0] = f(0, ctxs[0]);
+        else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < n; ++i) th.emplace_back([&, i] { rc[(size_t)i] = f(i, ctxs[(size_t)i]); });
+            for (auto& t : th) t.join();
+        }
+        for (int i = 0; i < n; ++i)
+            if (rc[(size_t)i] != WVA_OK) { err = "device " + std::to_string(ctxs[(size_t)i]->device) + ": " + wva_last_error(ctxs[(size_t)i]); return rc[(size_t)i]; }
+        return WVA_OK;
+    }
+};
+
+extern "C" {
+
+int wva_group_create(const int32_t* device_ids, int32_t n_devices, wva_group** out) {
+    if (!out) return fail(nullptr, WVA_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 64) return fail(nullptr, WVA_EINVAL, "bad device list");
+    const NcclApi& nc = nccl_api();
+    if (n_devices > 1 && !nc.ok) return fail(nullptr, WVA_ECUDA, "NCCL unavailable: " + nc.err);
+    wva_group* g = new wva_group;
+    for (int i = 0; i < n_devices; ++i) {
+        wva_ctx* c = nullptr;
+        int rc = wva_ctx_create(device_ids[i], &c);
+        if (rc != WVA_OK) { wva_group_destroy(g); return rc; }
+        g->ctxs.push_back(c);
+    }
+    if (nc.ok) {
+        std::vector<nccl_comm_t> comms((size_t)n_devices, nullptr);
+        std::vector<int> devs(device_ids, device_ids + n_devices);
+        int rc = nc.CommInitAll(comms.data(), n_devices, devs.data());
+        if (rc != 0) {
+            std::string msg = std::string("ncclCommInitAll: ") + nc.GetErrorString(rc);
+            wva_group_destroy(g);
+            return fail(nullptr, WVA_ECUDA, msg);
+        }
+        for (int i = 0; i < n_devices; ++i) {
+            wva_ctx* c = g->ctxs[(size_t)i];
+            c->comm = comms[(size_t)i]; c->comm_rank = i; c->comm_size = n_devices; c->comm_owned = true;
+        }
+    }
+    *out = g;
+    return WVA_OK;
+}
+
+void wva_group_destroy(wva_group* g) {
+    if (!g) return;
+    for (wva_ctx* c : g->ctxs) wva_ctx_destroy(c);
+    delete g;
+}
+
+int32_t wva_group_size(const wva_group* g) { return g ? (int32_t)g->ctxs.size() : 0; }
+wva_ctx* wva_group_ctx(wva_group* g, int32_t i) { return (g && i >= 0 && (size_t)i < g->ctxs.size()) ? g->ctxs[(size_t)i] : nullptr; }
+const char* wva_group_last_error(const wva_group* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+
+int wva_group_upload(wva_group* g, const wva_system_soa* host) {
+    if (!g || !host) return WVA_EINVAL;
+    int rc = g->each([&](int, wva_ctx* c) {
+        int r = wva_system_upload(c, host);
+        return r != WVA_OK ? r : wva_comm_shard(c);
+    });
+    if (rc == WVA_OK) { g->S = host->n_servers; g->A = host->n_accels; }
+    return rc;
+}
+
+int wva_group_analyze(wva_group* g, int32_t r_max, int32_t b_max, int32_t want_cube) {
+    if (!g) return WVA_EINVAL;
+    return g->each([&](int, wva_ctx* c) {
+        return r_max > 0 ? wva_analyze(c, r_max, b_max, want_cube) : wva_analyze_pairs(c, nullptr, nullptr);
+    });
+}
+
+int wva_group_pairs_fetch(wva_group* g, wva_alloc_soa* out, uint8_t* feasible) {
+    if (!g) return WVA_EINVAL;
+    return g->each([&](int, wva_ctx* c) { return wva_pairs_fetch(c, out, feasible); });   // each ctx writes its own rows
+}
+
+int wva_group_grid_fetch(wva_group* g, wva_grid_best* best) {
+    if (!g || !best) return WVA_EINVAL;
+    return g->each([&](int, wva_ctx* c) { return wva_grid_fetch(c, best + c->s0); });
+}
+
+int wva_group_solve(wva_group* g, const wva_optimizer_spec* spec, int32_t* chosen_acc, wva_alloc_soa* chosen) {
+    if (!g || !spec) return WVA_EINVAL;
+    // unlimited: every device solves and returns its own servers; limited: the gathered, replicated greedy
+    // yields the same assignment everywhere -- device 0 returns it
+    return g->each([&](int i, wva_ctx* c) {
+        const bool mine = spec->unlimited || i == 0;
+        return wva_solve(c, spec, mine ? chosen_acc : nullptr, mine ? chosen : nullptr);
+    });
+}
+
+int wva_group_allocate_by_type(wva_group* g, int64_t* count, float* cost) {
+    if (!g) return WVA_EINVAL;
+    return g->each([&](int i, wva_ctx* c) { return wva_allocate_by_type(c, i == 0 ? count : nullptr, i == 0 ? cost : nullptr); });
+}
+
+}  // extern "C"

@@ -1878,6 +1878,53 @@ __global__ void k_totals_merge(int T, int n_ranks, const unsigned char* __restri
     count[t] = c; cost[t] = k;
 }
 
+// ---- multi-rank exchange of the candidate records (limited mode) -----------------------------
+// One chunk per rank: {int first_pair, n_pairs, pad, pad} then SoA sections of `cap` records each
+// (replicas i64, batch i64, accelerator i32, 6 x f32, feasible u8 = 45 B per record).
+struct PairChunk {
+    long long* rep; long long* bat; int* acc; float* f[6]; unsigned char* fe; int* hdr;
+};
+__host__ __device__ __forceinline__ size_t pair_chunk_bytes(size_t cap) { return (16 + cap * 45 + 15) / 16 * 16; }
+__device__ __forceinline__ PairChunk pair_chunk_at(unsigned char* base, size_t cap) {
+    PairChunk c;
+    c.hdr = reinterpret_cast<int*>(base);
+    unsigned char* q = base + 16;
+    c.rep = reinterpret_cast<long long*>(q); q += cap * 8;
+    c.bat = reinterpret_cast<long long*>(q); q += cap * 8;
+    c.acc = reinterpret_cast<int*>(q); q += cap * 4;
+    for (int k = 0; k < 6; ++k) { c.f[k] = reinterpret_cast<float*>(q); q += cap * 4; }
+    c.fe = q;
+    return c;
+}
+__global__ void k_pairs_pack(DevAllocs pairs, const unsigned char* __restrict__ feasible, int firstPair, int nPairs, size_t cap,
+                             unsigned char* __restrict__ chunk) {
+    PairChunk c = pair_chunk_at(chunk, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { c.hdr[0] = firstPair; c.hdr[1] = nPairs; c.hdr[2] = 0; c.hdr[3] = 0; }
+    if (i >= nPairs) return;
+    const size_t g = (size_t)firstPair + i;
+    c.rep[i] = pairs.num_replicas[g]; c.bat[i] = pairs.batch_size[g]; c.acc[i] = pairs.acc[g];
+    c.f[0][i] = pairs.cost[g]; c.f[1][i] = pairs.value[g]; c.f[2][i] = pairs.itl[g];
+    c.f[3][i] = pairs.ttft[g]; c.f[4][i] = pairs.rho[g]; c.f[5][i] = pairs.max_arrv[g];
+    c.fe[i] = feasible[g];
+}
+// grid.y = source rank; rows of the calling rank itself are skipped (they are already in place)
+__global__ void k_pairs_unpack(unsigned char* __restrict__ gathered, size_t chunkBytes, size_t cap, int myRank, size_t nPairsAll,
+                               DevAllocs pairs, unsigned char* __restrict__ feasible) {
+    const int r = blockIdx.y;
+    if (r == myRank) return;
+    PairChunk c = pair_chunk_at(gathered + (size_t)r * chunkBytes, cap);
+    const int first = c.hdr[0], n = c.hdr[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t g = (size_t)first + i;
+        if (g >= nPairsAll) return;
+        pairs.num_replicas[g] = c.rep[i]; pairs.batch_size[g] = c.bat[i]; pairs.acc[g] = c.acc[i];
+        pairs.cost[g] = c.f[0][i]; pairs.value[g] = c.f[1][i]; pairs.itl[g] = c.f[2][i];
+        pairs.ttft[g] = c.f[3][i]; pairs.rho[g] = c.f[4][i]; pairs.max_arrv[g] = c.f[5][i];
+        feasible[g] = c.fe[i];
+    }
+}
+
 // ---- greedy ------------------------------------------------------------------------------
 
 // cmp.Compare for float32: NaN lowest, -0 == +0

@@ -9,14 +9,40 @@ Analyze needs no communication.  Optimize has ONE exchange step:
     so ranks all-gather their (server, accelerator) candidate rows and every rank runs the identical
     solve; totals are again reduced from per-shard partials.
 
-The functions below are backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the device path hands
-torch views of the library's own device buffers to the collectives (no staging copies).
+The collective itself lives INSIDE the library (wva_comm_init: ncclAllGather issued from C on the ctx
+stream, include/wva_b200.h "multi-GPU inside the library"); `attach_library_comm` only distributes the
+128-byte NCCL id over the process group the launcher already made.  The other functions are the
+host-driven variant (backend-agnostic: NCCL on GPUs, gloo in the CPU tests) kept for the CPU tests of the
+shard / gather / reduction logic and as a cross-check of the in-library exchange; they hand torch views of
+the library's own device buffers to the collectives (no staging copies) and enqueue every collective on
+the library's stream, so the library's next kernel is ordered after it.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import abi
+
+
+def attach_library_comm(ctx, device=None):
+    """Give `ctx` an NCCL communicator spanning the torch.distributed world: rank 0 creates the id
+    (wva_comm_unique_id), the process group broadcasts its 128 bytes, every rank calls wva_comm_init.
+    After this wva_allocate_by_type returns global totals and the limited solve gathers by itself."""
+    from . import binding
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if dist.get_backend() == "nccl":
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = torch.zeros(abi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(binding.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        uid = bytes(t.cpu().numpy().tobytes())
+    else:
+        box = [binding.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    ctx.comm_init(uid, rank, world)
+    return rank, world
 
 
 def shard_range(n_servers, rank, world):
@@ -46,11 +72,11 @@ class TotalsExchange:
     rank order (wva_type_totals_merge) back into that buffer.  Views and the gather buffer are
     created once."""
 
-    def __init__(self, ctx, n_types, device, stream=None):
+    def __init__(self, ctx, n_types, device):
         # the collective is enqueued on the library's own stream, where the partials were produced
-        # and where the merge kernel runs
+        # and where the merge kernel runs (ordering contract of wva_type_totals_merge)
         self.ctx, self.T = ctx, int(n_types)
-        self.stream = stream if stream is not None else torch.cuda.ExternalStream(ctx.stream(), device=device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
         self.world = dist.get_world_size()
         ptr, nbytes = ctx.type_totals_device()
         assert nbytes == 12 * self.T
@@ -71,9 +97,9 @@ class TotalsExchange:
         return self.count, self.cost
 
 
-def allreduce_totals_device(ctx, n_types, device, stream=None):
+def allreduce_totals_device(ctx, n_types, device):
     """One-shot form of TotalsExchange."""
-    return TotalsExchange(ctx, n_types, device, stream)()
+    return TotalsExchange(ctx, n_types, device)()
 
 
 def allreduce_totals_host(count, cost):
@@ -105,8 +131,16 @@ def gather_pair_rows_host(pairs, feasible, n_servers, n_accels, world):
 
 
 def gather_pair_rows_device(ctx, n_servers, n_accels, world, device):
-    """Limited mode on GPUs: all-gather the candidate rows in place in the library's device arrays
-    (wva_pairs_device), then mark them complete (wva_pairs_commit)."""
+    """Limited mode on GPUs, host-driven variant: all-gather the candidate rows in place in the library's
+    device arrays (wva_pairs_device), then mark them complete (wva_pairs_commit).  The collectives run on
+    the library's stream (and wva_pairs_commit waits for the device), so the greedy kernels that follow can
+    never see half-gathered rows."""
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream(), device=device)):
+        _gather_pair_rows_device(ctx, n_servers, n_accels, world, device)
+    ctx.pairs_commit()
+
+
+def _gather_pair_rows_device(ctx, n_servers, n_accels, world, device):
     ptrs = ctx.pairs_device()
     n = n_servers * n_accels
     bounds = [shard_range(n_servers, r, world) for r in range(world)]
@@ -121,4 +155,3 @@ def gather_pair_rows_device(ctx, n_servers, n_accels, world, device):
             for r, (f, c) in enumerate(bounds):      # shards differ by one server: broadcast per owner, in place
                 if c:
                     dist.broadcast(full[f * n_accels:(f + c) * n_accels], src=r)
-    ctx.pairs_commit()

@@ -57,6 +57,16 @@ class SystemImage:
             setattr(out, name, getattr(self, name)[first:first + count].copy())
         return out
 
+    def take(self, servers):
+        """A new image holding the listed servers (in that order) and the full replicated tables."""
+        idx = np.asarray(servers, dtype=np.int64)
+        out = SystemImage(len(idx), self.A, self.M, self.T)
+        for name, _ in abi.ACC_FIELDS + abi.TYPE_FIELDS + abi.PERF_FIELDS:
+            setattr(out, name, getattr(self, name).copy())
+        for name, _ in abi.SRV_FIELDS:
+            setattr(out, name, getattr(self, name)[idx].copy())
+        return out
+
     # ------------------------------------------------------------------------------
     @classmethod
     def from_spec(cls, spec):

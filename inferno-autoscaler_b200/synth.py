@@ -21,10 +21,12 @@ SERVICE_CLASSES = [(24.0, 500.0, 1), (80.0, 1000.0, 5), (200.0, 2000.0, 10)]
 
 def make_system(n_servers, n_accels, seed, n_types=None, one_model_per_server=True, n_models=None,
                 edge_fraction=0.02, tps_fraction=0.10, zero_load_fraction=0.02, keep_fraction=0.10,
-                max_pair_batch=512):
+                max_pair_batch=512, out_tokens_min=32):
     """Random system image.  `max_pair_batch` bounds N = maxBatch*atTokens/outTokens of the
     reference sizing path (pkg/core/allocation.go:85) through a server-level batch override, so
-    one pathological pair cannot dominate a whole run (N has no upper bound in the reference)."""
+    one pathological pair cannot dominate a whole run (N has no upper bound in the reference).
+    `max_pair_batch=0, out_tokens_min=1` is SURVEY 8(d)'s generator as written ("un-tamed": out_tokens
+    from {1..1024}, no bound on N -- N reaches maxBatch*atTokens = 262 144, K = 11 N = 2.9 M states)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     S, A = int(n_servers), int(n_accels)
     T = int(n_types) if n_types else A
@@ -62,7 +64,7 @@ def make_system(n_servers, n_accels, seed, n_types=None, one_model_per_server=Tr
     arrival[rng.uniform(0, 1, S) < zero_load_fraction] = 0.0
     img.srv_arrival_rpm[:] = arrival.astype(np.float32)
     img.srv_in_tokens[:] = rng.integers(16, 4097, S, dtype=np.int32)
-    img.srv_out_tokens[:] = rng.integers(32, 1025, S, dtype=np.int32)
+    img.srv_out_tokens[:] = rng.integers(int(out_tokens_min), 1025, S, dtype=np.int32)
     edge = rng.uniform(0, 1, S)
     img.srv_out_tokens[edge < edge_fraction / 2] = 1                      # single output token
     img.srv_in_tokens[(edge >= edge_fraction / 2) & (edge < edge_fraction)] = 0   # decode only

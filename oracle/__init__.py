@@ -51,10 +51,16 @@ def lib():
         L.wvao_transition_penalty.argtypes = [C.c_int32, C.c_int64, C.c_float, C.c_int32, C.c_int64, C.c_float]
         L.wvao_queue_analyze.argtypes = [C.c_int32, C.c_void_p, abi.f32p, C.c_void_p, abi.u8p]
         L.wvao_queue_size.argtypes = [C.c_int32, C.c_void_p, abi.f32p, abi.f32p, C.c_void_p, abi.f32p, abi.u8p]
+        L.wvao_queue_analyze_mt.argtypes = [C.c_int32, C.c_void_p, abi.f32p, C.c_void_p, abi.u8p, C.c_int]
+        L.wvao_grid_candidates.argtypes = [C.POINTER(abi.SystemSoa), C.c_int64, abi.i32p, abi.i32p, abi.i32p, abi.i32p,
+                                           C.c_void_p, abi.u8p, C.c_int]
         L.wvao_analyze_pairs.argtypes = [C.POINTER(abi.SystemSoa), C.POINTER(abi.AllocSoa), abi.u8p, C.c_int,
                                          C.POINTER(C.c_uint64)]
         L.wvao_analyze_grid.argtypes = [C.POINTER(abi.SystemSoa), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.wvao_grid_row_values.argtypes = [C.POINTER(abi.SystemSoa), C.c_int32, C.c_int32, C.c_int32, abi.f32p]
+        L.wvao_grid_rows_feasible.argtypes = [C.POINTER(abi.SystemSoa), C.c_int64, abi.i32p, abi.i32p, abi.i32p, abi.i32p,
+                                              abi.i32p, abi.i32p, C.c_int]
         L.wvao_solve.argtypes = [C.POINTER(abi.SystemSoa), C.POINTER(abi.AllocSoa), abi.u8p,
                                  C.POINTER(abi.OptimizerSpec), abi.i32p, C.POINTER(abi.AllocSoa)]
         L.wvao_allocate_by_type.argtypes = [C.POINTER(abi.SystemSoa), C.c_int32, C.c_int32, abi.i32p,
@@ -201,14 +207,26 @@ def effective_concurrency(serv_time, alpha, beta, gamma, delta, in_tok, out_tok,
                                                        C.c_float(gamma), C.c_float(delta), in_tok, out_tok, max_batch))
 
 
-def queue_analyze(cfgs, rates):
+def queue_analyze(cfgs, rates, threads=1):
     cfgs = np.ascontiguousarray(cfgs, dtype=abi.QUEUE_CONFIG_DTYPE)
     rates = np.ascontiguousarray(rates, dtype=np.float32)
     n = len(cfgs)
     metrics = np.zeros(n, dtype=abi.METRICS_DTYPE)
     status = np.zeros(n, dtype=np.uint8)
-    lib().wvao_queue_analyze(n, cfgs.ctypes.data, abi.ptr(rates, C.c_float), metrics.ctypes.data,
-                             abi.ptr(status, C.c_uint8))
+    lib().wvao_queue_analyze_mt(n, cfgs.ctypes.data, abi.ptr(rates, C.c_float), metrics.ctypes.data,
+                                abi.ptr(status, C.c_uint8), int(threads))
+    return metrics, status
+
+
+def grid_candidates(img, s, a, r, b, threads=1):
+    """The sweep's candidates (s, a, r, b) one by one through the reference API -> (metrics, status)."""
+    sysc = img.c_struct()
+    arr = [np.ascontiguousarray(x, dtype=np.int32) for x in (s, a, r, b)]
+    n = len(arr[0])
+    metrics = np.zeros(n, dtype=abi.METRICS_DTYPE)
+    status = np.zeros(n, dtype=np.uint8)
+    lib().wvao_grid_candidates(C.byref(sysc), n, *[abi.ptr(x, C.c_int32) for x in arr], metrics.ctypes.data,
+                               abi.ptr(status, C.c_uint8), int(threads))
     return metrics, status
 
 
@@ -248,6 +266,25 @@ def analyze_grid(img, r_max, b_max, s0=0, s1=None, want_cube=True, threads=1):
                             cube.ctypes.data if want_cube else None,
                             status.ctypes.data if want_cube else None, threads, C.byref(steps))
     return best, cube, status, steps.value
+
+
+def grid_row_values(img, r_max, s0=0, s1=None):
+    """value of every sweep row (s, a, r) -> float32 [ns, A, r_max] (NaN where the pair is unusable)."""
+    s1 = img.S if s1 is None else s1
+    sysc = img.c_struct()
+    out = np.zeros((s1 - s0) * img.A * r_max, dtype=np.float32)
+    lib().wvao_grid_row_values(C.byref(sysc), s0, s1, r_max, abi.ptr(out, C.c_float))
+    return out.reshape(s1 - s0, img.A, r_max)
+
+
+def grid_rows_feasible(img, s, a, r, b_lo, b_hi, threads=1):
+    """feasible-candidate count of each listed row over b in [b_lo, b_hi] (reference API per candidate)."""
+    sysc = img.c_struct()
+    arr = [np.ascontiguousarray(x, dtype=np.int32) for x in (s, a, r, b_lo, b_hi)]
+    n = len(arr[0])
+    out = np.zeros(n, dtype=np.int32)
+    lib().wvao_grid_rows_feasible(C.byref(sysc), n, *[abi.ptr(x, C.c_int32) for x in arr], abi.ptr(out, C.c_int32), int(threads))
+    return out
 
 
 def solve(img, pairs, feasible, unlimited=True, delayed_best_effort=False, policy=abi.POLICY_NONE):

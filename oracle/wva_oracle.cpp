@@ -726,19 +726,22 @@ void bestEffort(GreedyState& g, const std::vector<ServerEntry*>& unallocated, in
 // =======================================================================================
 extern "C" {
 
-int wvao_queue_analyze(int32_t n, const wva_queue_config* cfg, const float* rate, wva_metrics* metrics, uint8_t* status) {
-    for (int32_t i = 0; i < n; i++) {
+int wvao_queue_analyze_mt(int32_t n, const wva_queue_config* cfg, const float* rate, wva_metrics* metrics, uint8_t* status, int threads) {
+    parallelFor(n, threads, [&](int64_t i) {
         std::memset(&metrics[i], 0, sizeof(wva_metrics));
         const wva_queue_config& c = cfg[i];
         if (!configOk(c.max_batch_size, c.max_queue_size, c.avg_input_tokens, c.avg_output_tokens)) {
-            status[i] = WVA_CAND_ERR_CONFIG; continue;
+            status[i] = WVA_CAND_ERR_CONFIG; return;
         }
         QueueAnalyzer qa;
         buildModel(qa, c.max_batch_size, c.max_queue_size, ServiceParms{c.alpha, c.beta, c.gamma, c.delta},
                    c.avg_input_tokens, c.avg_output_tokens);
         status[i] = (uint8_t)analyze(qa, rate[i], &metrics[i]);
-    }
+    });
     return WVA_OK;
+}
+int wvao_queue_analyze(int32_t n, const wva_queue_config* cfg, const float* rate, wva_metrics* metrics, uint8_t* status) {
+    return wvao_queue_analyze_mt(n, cfg, rate, metrics, status, 1);
 }
 
 int wvao_queue_size(int32_t n, const wva_queue_config* cfg, const float* target, float* rates, wva_metrics* metrics,
@@ -852,16 +855,14 @@ float wvao_transition_penalty(int32_t aAcc, int64_t aRep, float aCost, int32_t b
 int wvao_analyze_pairs(const wva_system_soa* sys, wva_alloc_soa* out, uint8_t* feasible, int threads, uint64_t* steps) {
     const int32_t S = sys->n_servers, A = sys->n_accels;
     std::atomic<uint64_t> total{0};
-    parallelFor(S, threads, [&](int64_t s) {
+    parallelFor((int64_t)S * A, threads, [&](int64_t i) {      // one work item per (server, accelerator) pair
         uint64_t st = 0;
-        for (int32_t a = 0; a < A; a++) {
-            Alloc al;
-            bool ok = calculatePair(sys, (int32_t)s, a, &al, &st);
-            size_t i = (size_t)s * A + a;
-            if (!ok) al = Alloc{};
-            storeAlloc(out, i, al);
-            feasible[i] = ok ? 1 : 0;
-        }
+        const int32_t s = (int32_t)(i / A), a = (int32_t)(i % A);
+        Alloc al;
+        bool ok = calculatePair(sys, s, a, &al, &st);
+        if (!ok) al = Alloc{};
+        storeAlloc(out, (size_t)i, al);
+        feasible[i] = ok ? 1 : 0;
         total += st;
     });
     if (steps) *steps = total.load();
@@ -869,78 +870,147 @@ int wvao_analyze_pairs(const wva_system_soa* sys, wva_alloc_soa* out, uint8_t* f
 }
 
 // Candidate sweep oracle: the reference's own QueueAnalyzer API at (N=b, maxQueue=10b, rate=total/r).
+// One candidate = one fresh NewQueueAnalyzer + Analyze (queueanalyzer.go:87-174); SLO tests as in
+// allocation.go:134-139 / queueanalyzer.go:231-246; value = TransitionPenalty of the candidate's cost.
+struct GridCand {
+    wva_metrics m; int status; bool feas; float value, cost, ttft, itl; uint64_t steps;
+};
+static void gridCandidate(const wva_system_soa* sys, int32_t s, int32_t a, int32_t r, int32_t b, GridCand* o) {
+    const int32_t A = sys->n_accels;
+    std::memset(&o->m, 0, sizeof(o->m));
+    o->feas = false; o->value = 0; o->cost = 0; o->ttft = 0; o->itl = 0; o->steps = 0;
+    const bool pairOk = pairLookupsOk(sys, s, a) && isCandidateAccel(sys, s, a);
+    const float arrival = sys->srv_arrival_rpm[s];
+    const int64_t inTok = sys->srv_in_tokens[s], outTok = sys->srv_out_tokens[s];
+    const float sloTTFT = sys->srv_slo_ttft[s], sloITL = sys->srv_slo_itl[s], sloTPS = sys->srv_slo_tps[s];
+    float rate = 0, rateTPS = 0;
+    if (!pairOk) { o->status = WVA_CAND_ERR_PAIR; return; }
+    if (!configOk(b, (int64_t)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, inTok, outTok) || sloTTFT < 0 || sloITL < 0 || sloTPS < 0) {
+        o->status = WVA_CAND_ERR_CONFIG; return;
+    }
+    const size_t pi = (size_t)sys->srv_model[s] * A + a;
+    const ServiceParms sp{sys->perf_alpha[pi], sys->perf_beta[pi], sys->perf_gamma[pi], sys->perf_delta[pi]};
+    const int64_t ninst = numInstances(sys, sys->srv_model[s], a);
+    QueueAnalyzer qa;
+    buildModel(qa, b, (int64_t)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, sp, inTok, outTok);
+    float totalRate = (sloTPS == 0) ? arrival / 60.0f : sloTPS / (float)outTok;   // allocation.go:134-139
+    rate = totalRate / (float)r;
+    o->status = analyze(qa, rate, &o->m);
+    o->steps = qa.model.steps;
+    float lamMax = qa.rateMax / 1000.0f;
+    rateTPS = (lamMax * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;   // TargetRate.RateTargetTPS, :231-234,:246
+    if (o->status != WVA_CAND_OK) { std::memset(&o->m, 0, sizeof(o->m)); return; }
+    o->ttft = o->m.avg_wait_time + o->m.avg_prefill_time;
+    o->itl = o->m.avg_token_time;
+    o->feas = (!(sloTTFT > 0) || o->ttft <= sloTTFT) && (!(sloITL > 0) || o->itl <= sloITL) &&
+              (!(sloTPS > 0) || rate <= rateTPS) && ((int64_t)r >= (int64_t)sys->srv_min_replicas[s]);
+    if (o->feas) {
+        Alloc cand; cand.acc = a; cand.numReplicas = r;
+        cand.cost = sys->acc_cost[a] * (float)go_muli(ninst, r);
+        o->cost = cand.cost;
+        float value = transitionPenalty(sys->srv_cur_acc[s], sys->srv_cur_replicas[s], sys->srv_cur_cost[s], cand);
+        o->value = value + 0.0f;   // canonical +0
+    }
+}
+
 // server range [s0, s1) so callers can bound the work.  best/cube/status indexed as in wva_analyze_grid
-// but relative to s0.
+// but relative to s0.  Host threads work on (server, accelerator, replicas) rows; the per-server winner is
+// then reduced in the loop order of the sweep (a, r, b ascending, strict <), so the result does not depend
+// on the thread count.
 int wvao_analyze_grid(const wva_system_soa* sys, int32_t s0, int32_t s1, int32_t r_max, int32_t b_max,
                       wva_grid_best* best, wva_metrics* cube, uint8_t* status, int threads, uint64_t* steps) {
     const int32_t A = sys->n_accels;
+    const int64_t ns = s1 - s0;
+    const int64_t nRows = ns * A * r_max;
     std::atomic<uint64_t> total{0};
-    parallelFor((int64_t)(s1 - s0), threads, [&](int64_t si) {
+    struct RowBest { bool have; wva_grid_best bb; };
+    std::vector<RowBest> rows(best ? (size_t)nRows : 0);
+    parallelFor(nRows, threads, [&](int64_t row) {
+        const int32_t r = (int32_t)(row % r_max) + 1;
+        const int32_t a = (int32_t)((row / r_max) % A);
+        const int64_t si = row / ((int64_t)r_max * A);
         const int32_t s = s0 + (int32_t)si;
         uint64_t st = 0;
-        wva_grid_best bb; std::memset(&bb, 0, sizeof(bb)); bb.acc = -1;
-        bool have = false;
-        const float arrival = sys->srv_arrival_rpm[s];
-        const int64_t inTok = sys->srv_in_tokens[s], outTok = sys->srv_out_tokens[s];
-        const float sloTTFT = sys->srv_slo_ttft[s], sloITL = sys->srv_slo_itl[s], sloTPS = sys->srv_slo_tps[s];
-        for (int32_t a = 0; a < A; a++) {
-            const bool pairOk = pairLookupsOk(sys, s, a) && isCandidateAccel(sys, s, a);
-            ServiceParms sp{0, 0, 0, 0};
-            int64_t ninst = 1;
-            if (pairOk) {
-                size_t pi = (size_t)sys->srv_model[s] * A + a;
-                sp = ServiceParms{sys->perf_alpha[pi], sys->perf_beta[pi], sys->perf_gamma[pi], sys->perf_delta[pi]};
-                ninst = numInstances(sys, sys->srv_model[s], a);
-            }
-            for (int32_t r = 1; r <= r_max; r++) {
-                for (int32_t b = 1; b <= b_max; b++) {
-                    size_t ci = (((size_t)si * A + a) * r_max + (r - 1)) * b_max + (b - 1);
-                    wva_metrics m; std::memset(&m, 0, sizeof(m));
-                    int stt;
-                    bool feas = false;
-                    float rate = 0, rateTPS = 0;
-                    if (!pairOk) stt = WVA_CAND_ERR_PAIR;
-                    else if (!configOk(b, (int64_t)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, inTok, outTok) ||
-                             sloTTFT < 0 || sloITL < 0 || sloTPS < 0) stt = WVA_CAND_ERR_CONFIG;
-                    else {
-                        QueueAnalyzer qa;
-                        buildModel(qa, b, (int64_t)b * WVA_MAX_QUEUE_TO_BATCH_RATIO, sp, inTok, outTok);
-                        float totalRate = (sloTPS == 0) ? arrival / 60.0f : sloTPS / (float)outTok;   // allocation.go:134-139
-                        rate = totalRate / (float)r;
-                        stt = analyze(qa, rate, &m);
-                        st += qa.model.steps;
-                        float lamMax = qa.rateMax / 1000.0f;
-                        rateTPS = (lamMax * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;   // TargetRate.RateTargetTPS, :231-234,:246
-                    }
-                    if (stt == WVA_CAND_OK) {
-                        float ttft = m.avg_wait_time + m.avg_prefill_time;
-                        float itl = m.avg_token_time;
-                        feas = (!(sloTTFT > 0) || ttft <= sloTTFT) && (!(sloITL > 0) || itl <= sloITL) &&
-                               (!(sloTPS > 0) || rate <= rateTPS) && ((int64_t)r >= (int64_t)sys->srv_min_replicas[s]);
-                        if (feas) {
-                            Alloc cand; cand.acc = a; cand.numReplicas = r;
-                            cand.cost = sys->acc_cost[a] * (float)go_muli(ninst, r);
-                            float value = transitionPenalty(sys->srv_cur_acc[s], sys->srv_cur_replicas[s], sys->srv_cur_cost[s], cand);
-                            value = value + 0.0f;   // canonical +0
-                            if (value == value) {   // NaN values are never selected
-                                bool better = !have || value < bb.value;   // (value, a, r, b) lexicographic, loops ascend
-                                if (better) {
-                                    have = true;
-                                    bb.acc = a; bb.replicas = r; bb.batch = b; bb.cost = cand.cost; bb.value = value;
-                                    bb.itl = itl; bb.ttft = ttft; bb.rho = m.rho;
-                                }
-                            }
-                        }
-                    } else std::memset(&m, 0, sizeof(m));
-                    if (cube) cube[ci] = m;
-                    if (status) status[ci] = (uint8_t)(stt | (feas ? WVA_CAND_FEASIBLE : 0));
+        RowBest rb; rb.have = false; std::memset(&rb.bb, 0, sizeof(rb.bb)); rb.bb.acc = -1;
+        for (int32_t b = 1; b <= b_max; b++) {
+            const size_t ci = (size_t)row * b_max + (b - 1);
+            GridCand gc;
+            gridCandidate(sys, s, a, r, b, &gc);
+            st += gc.steps;
+            if (gc.feas && gc.value == gc.value) {          // NaN values are never selected
+                if (!rb.have || gc.value < rb.bb.value) {
+                    rb.have = true;
+                    rb.bb.acc = a; rb.bb.replicas = r; rb.bb.batch = b; rb.bb.cost = gc.cost; rb.bb.value = gc.value;
+                    rb.bb.itl = gc.itl; rb.bb.ttft = gc.ttft; rb.bb.rho = gc.m.rho;
                 }
             }
+            if (cube) cube[ci] = gc.m;
+            if (status) status[ci] = (uint8_t)(gc.status | (gc.feas ? WVA_CAND_FEASIBLE : 0));
         }
-        if (best) best[si] = bb;
+        if (best) rows[(size_t)row] = rb;
         total += st;
     });
+    if (best) {
+        for (int64_t si = 0; si < ns; si++) {
+            wva_grid_best bb; std::memset(&bb, 0, sizeof(bb)); bb.acc = -1;
+            bool have = false;
+            for (int64_t k = 0; k < (int64_t)A * r_max; k++) {     // (a, r) ascending
+                const RowBest& rb = rows[(size_t)(si * A * r_max + k)];
+                if (rb.have && (!have || rb.bb.value < bb.value)) { have = true; bb = rb.bb; }
+            }
+            best[si] = bb;
+        }
+    }
     if (steps) *steps = total.load();
+    return WVA_OK;
+}
+
+// A list of sweep candidates (s, a, r, b), each evaluated exactly like the loop body above.
+// out_value / out_feasible may be NULL.
+int wvao_grid_candidates(const wva_system_soa* sys, int64_t n, const int32_t* s, const int32_t* a, const int32_t* r,
+                         const int32_t* b, wva_metrics* metrics, uint8_t* status, int threads) {
+    parallelFor(n, threads, [&](int64_t i) {
+        GridCand gc;
+        gridCandidate(sys, s[i], a[i], r[i], b[i], &gc);
+        metrics[i] = gc.m;
+        status[i] = (uint8_t)(gc.status | (gc.feas ? WVA_CAND_FEASIBLE : 0));
+    });
+    return WVA_OK;
+}
+
+// value (TransitionPenalty of cost = acc.Cost * float32(numInstances * r), canonical +0) of every sweep row
+// (s, a, r), s in [s0, s1): what orders the candidates of a server.  NaN for rows whose pair lookups fail.
+int wvao_grid_row_values(const wva_system_soa* sys, int32_t s0, int32_t s1, int32_t r_max, float* value) {
+    const int32_t A = sys->n_accels;
+    for (int32_t s = s0; s < s1; s++)
+        for (int32_t a = 0; a < A; a++) {
+            const bool pairOk = pairLookupsOk(sys, s, a) && isCandidateAccel(sys, s, a);
+            const int64_t ninst = pairOk ? numInstances(sys, sys->srv_model[s], a) : 1;
+            for (int32_t r = 1; r <= r_max; r++) {
+                float v = std::numeric_limits<float>::quiet_NaN();
+                if (pairOk) {
+                    Alloc cand; cand.acc = a; cand.numReplicas = r;
+                    cand.cost = sys->acc_cost[a] * (float)go_muli(ninst, r);
+                    v = transitionPenalty(sys->srv_cur_acc[s], sys->srv_cur_replicas[s], sys->srv_cur_cost[s], cand) + 0.0f;
+                }
+                value[((size_t)(s - s0) * A + a) * r_max + (r - 1)] = v;
+            }
+        }
+    return WVA_OK;
+}
+
+// For each listed row (s, a, r): how many of its candidates b in [b_lo, b_hi] the reference API finds feasible.
+int wvao_grid_rows_feasible(const wva_system_soa* sys, int64_t n, const int32_t* s, const int32_t* a, const int32_t* r,
+                            const int32_t* b_lo, const int32_t* b_hi, int32_t* n_feasible, int threads) {
+    parallelFor(n, threads, [&](int64_t i) {
+        int32_t cnt = 0;
+        for (int32_t b = b_lo[i]; b <= b_hi[i]; b++) {
+            GridCand gc;
+            gridCandidate(sys, s[i], a[i], r[i], b, &gc);
+            if (gc.feas && gc.value == gc.value) cnt++;
+        }
+        n_feasible[i] = cnt;
+    });
     return WVA_OK;
 }
 
