@@ -6,8 +6,15 @@
 // go/pkg; build with CGO_ENABLED=1 (the reference Dockerfile:25 sets 0) and
 //   CGO_CFLAGS=-I<repo>/include  CGO_LDFLAGS="-L<repo>/inferno-autoscaler_b200 -lwva_b200"
 //
-// cgo pointer rules: every call passes Go-allocated slices for the duration of the call only; the
-// library copies what it needs (wva_b200.h "Conventions") and retains no Go pointer.
+// cgo pointer rules (cmd/cgo "Passing pointers"):
+//   (1) the library retains no Go pointer after a call returns (wva_b200.h "Conventions": it copies);
+//   (2) a Go pointer passed to C must not point at memory that itself holds Go pointers.  The struct forms
+//       wva_system_upload / wva_analyze_pairs / wva_solve take a struct OF pointers: a Go-allocated
+//       C.wva_system_soa whose fields point at Go slices violates (2) and panics under the default
+//       GODEBUG=cgocheck=1 ("cgo argument has Go pointer to unpinned Go pointer").  This binding therefore
+//       calls the *_arrays forms of the header, where every slice is its own argument (a pointer to
+//       pointer-free memory needs no pinning).  The only struct-of-pointers call is Group.Upload, which builds
+//       the struct in C memory and pins every slice with runtime.Pinner for the duration of the call.
 package native
 
 /*
@@ -62,18 +69,6 @@ func newAllocs(n int) *Allocs {
 		Rho: make([]float32, n), MaxArrv: make([]float32, n)}
 }
 
-func (a *Allocs) c() C.wva_alloc_soa {
-	return C.wva_alloc_soa{
-		acc:          (*C.int32_t)(unsafe.Pointer(&a.Acc[0])),
-		num_replicas: (*C.int64_t)(unsafe.Pointer(&a.NumReplicas[0])),
-		batch_size:   (*C.int64_t)(unsafe.Pointer(&a.BatchSize[0])),
-		cost:         (*C.float)(unsafe.Pointer(&a.Cost[0])), value: (*C.float)(unsafe.Pointer(&a.Value[0])),
-		itl: (*C.float)(unsafe.Pointer(&a.ITL[0])), ttft: (*C.float)(unsafe.Pointer(&a.TTFT[0])),
-		rho:                        (*C.float)(unsafe.Pointer(&a.Rho[0])),
-		max_arrv_rate_per_replica: (*C.float)(unsafe.Pointer(&a.MaxArrv[0])),
-	}
-}
-
 // Context wraps wva_ctx: one per process (creation builds the CUDA context), one call at a time —
 // the same constraint the reference has through its package globals (pkg/core/system.go:12).
 type Context struct {
@@ -119,20 +114,15 @@ func u8p(s []uint8) *C.uint8_t  { if len(s) == 0 { return nil }; return (*C.uint
 func (c *Context) Upload(img *SystemImage) error {
 	c.mu.Lock()
 	defer c.mu.Unlock()
-	h := C.wva_system_soa{
-		n_servers: C.int32_t(img.S), n_accels: C.int32_t(img.A), n_models: C.int32_t(img.M), n_types: C.int32_t(img.T),
-		acc_cost: f32p(img.AccCost), acc_multiplicity: i32p(img.AccMultiplicity), acc_type: i32p(img.AccType),
-		type_capacity: i64p(img.TypeCapacity),
-		perf_alpha:    f32p(img.PerfAlpha), perf_beta: f32p(img.PerfBeta), perf_gamma: f32p(img.PerfGamma), perf_delta: f32p(img.PerfDelta),
-		perf_max_batch: i32p(img.PerfMaxBatch), perf_at_tokens: i32p(img.PerfAtTokens), perf_acc_count: i32p(img.PerfAccCount),
-		perf_valid: u8p(img.PerfValid),
-		srv_model:  i32p(img.SrvModel), srv_arrival_rpm: f32p(img.SrvArrivalRPM), srv_in_tokens: i32p(img.SrvInTokens),
-		srv_out_tokens: i32p(img.SrvOutTokens), srv_slo_ttft: f32p(img.SrvSloTTFT), srv_slo_itl: f32p(img.SrvSloITL),
-		srv_slo_tps: f32p(img.SrvSloTPS), srv_target_valid: u8p(img.SrvTargetValid), srv_priority: i32p(img.SrvPriority),
-		srv_min_replicas: i32p(img.SrvMinReplicas), srv_max_batch: i32p(img.SrvMaxBatch), srv_keep_acc: u8p(img.SrvKeepAcc),
-		srv_cur_acc: i32p(img.SrvCurAcc), srv_cur_replicas: i32p(img.SrvCurReplicas), srv_cur_cost: f32p(img.SrvCurCost),
-	}
-	return c.err(C.wva_system_upload(c.ctx, &h), "wva_system_upload")
+	rc := C.wva_system_upload_arrays(c.ctx, C.int32_t(img.S), C.int32_t(img.A), C.int32_t(img.M), C.int32_t(img.T),
+		f32p(img.AccCost), i32p(img.AccMultiplicity), i32p(img.AccType), i64p(img.TypeCapacity),
+		f32p(img.PerfAlpha), f32p(img.PerfBeta), f32p(img.PerfGamma), f32p(img.PerfDelta),
+		i32p(img.PerfMaxBatch), i32p(img.PerfAtTokens), i32p(img.PerfAccCount), u8p(img.PerfValid),
+		i32p(img.SrvModel), f32p(img.SrvArrivalRPM), i32p(img.SrvInTokens), i32p(img.SrvOutTokens),
+		f32p(img.SrvSloTTFT), f32p(img.SrvSloITL), f32p(img.SrvSloTPS), u8p(img.SrvTargetValid),
+		i32p(img.SrvPriority), i32p(img.SrvMinReplicas), i32p(img.SrvMaxBatch), u8p(img.SrvKeepAcc),
+		i32p(img.SrvCurAcc), i32p(img.SrvCurReplicas), f32p(img.SrvCurCost))
+	return c.err(rc, "wva_system_upload_arrays")
 }
 
 // AnalyzePairs replaces Server.Calculate for all servers: S*A records + feasible flags.
@@ -144,8 +134,9 @@ func (c *Context) AnalyzePairs(s, a int) (*Allocs, []uint8, error) {
 		return newAllocs(0), nil, nil
 	}
 	out, fe := newAllocs(n), make([]uint8, n)
-	co := out.c()
-	if err := c.err(C.wva_analyze_pairs(c.ctx, &co, u8p(fe)), "wva_analyze_pairs"); err != nil {
+	rc := C.wva_analyze_pairs_arrays(c.ctx, i32p(out.Acc), i64p(out.NumReplicas), i64p(out.BatchSize), f32p(out.Cost), f32p(out.Value),
+		f32p(out.ITL), f32p(out.TTFT), f32p(out.Rho), f32p(out.MaxArrv), u8p(fe))
+	if err := c.err(rc, "wva_analyze_pairs_arrays"); err != nil {
 		return nil, nil, err
 	}
 	return out, fe, nil
@@ -156,13 +147,14 @@ func (c *Context) Solve(s int, unlimited, delayedBestEffort bool, policy int) ([
 	c.mu.Lock()
 	defer c.mu.Unlock()
 	b := func(v bool) C.int32_t { if v { return 1 }; return 0 }
-	spec := C.wva_optimizer_spec{unlimited: b(unlimited), delayed_best_effort: b(delayedBestEffort), saturation_policy: C.int32_t(policy)}
 	if s == 0 {
 		return nil, newAllocs(0), 0, nil
 	}
 	key, out := make([]int32, s), newAllocs(s)
-	co := out.c()
-	if err := c.err(C.wva_solve(c.ctx, &spec, i32p(key), &co), "wva_solve"); err != nil {
+	rc := C.wva_solve_arrays(c.ctx, b(unlimited), b(delayedBestEffort), C.int32_t(policy), i32p(key),
+		i32p(out.Acc), i64p(out.NumReplicas), i64p(out.BatchSize), f32p(out.Cost), f32p(out.Value),
+		f32p(out.ITL), f32p(out.TTFT), f32p(out.Rho), f32p(out.MaxArrv))
+	if err := c.err(rc, "wva_solve_arrays"); err != nil {
 		return nil, nil, 0, err
 	}
 	return key, out, int64(C.wva_solution_time_usec(c.ctx)), nil
@@ -192,6 +184,33 @@ func (c *Context) SetShard(first, count int) error {
 	c.mu.Lock()
 	defer c.mu.Unlock()
 	return c.err(C.wva_set_shard(c.ctx, C.int32_t(first), C.int32_t(count)), "wva_set_shard")
+}
+
+// CommUniqueID / CommInit / CommShard: one process per GPU.  Rank 0 makes the 128-byte id, the caller
+// distributes it (any transport), every rank attaches; from then on AllocateByType returns GLOBAL totals
+// (the library runs the NCCL all-gather and the rank-order sum) and a limited Solve gathers the candidate
+// rows itself.
+func CommUniqueID() ([]byte, error) {
+	id := make([]byte, C.WVA_COMM_ID_BYTES)
+	if rc := C.wva_comm_unique_id(unsafe.Pointer(&id[0])); rc != C.WVA_OK {
+		return nil, fmt.Errorf("wva_comm_unique_id: %d: %s", int(rc), C.GoString(C.wva_last_error(nil)))
+	}
+	return id, nil
+}
+
+func (c *Context) CommInit(id []byte, rank, nRanks int) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	if len(id) != C.WVA_COMM_ID_BYTES {
+		return fmt.Errorf("communicator id must have %d bytes", int(C.WVA_COMM_ID_BYTES))
+	}
+	return c.err(C.wva_comm_init(c.ctx, unsafe.Pointer(&id[0]), C.int32_t(rank), C.int32_t(nRanks)), "wva_comm_init")
+}
+
+func (c *Context) CommShard() error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return c.err(C.wva_comm_shard(c.ctx), "wva_comm_shard")
 }
 
 // TypeTotalsMerge sums the per-rank totals blocks that the host all-gathered (device memory,
@@ -258,4 +277,76 @@ func (c *Context) QueueSize(cfg []QueueConfig, target []float32) (rates []float3
 		(*C.wva_metrics)(unsafe.Pointer(&m[0])), f32p(achieved), u8p(status))
 	err = c.err(rc, "wva_queue_size")
 	return
+}
+
+// Group wraps wva_group: ONE process (the single reconcile goroutine of
+// internal/controller/variantautoscaling_controller.go:143-166) driving every GPU of the box.  Servers are
+// sharded over the devices by the library; outputs have the full extent; totals are global.
+type Group struct {
+	mu sync.Mutex
+	g  *C.wva_group
+	n  int
+}
+
+func NewGroup(devices []int32) (*Group, error) {
+	if len(devices) == 0 {
+		return nil, fmt.Errorf("no devices")
+	}
+	var g *C.wva_group
+	if rc := C.wva_group_create(i32p(devices), C.int32_t(len(devices)), &g); rc != C.WVA_OK {
+		return nil, fmt.Errorf("wva_group_create: %d: %s", int(rc), C.GoString(C.wva_last_error(nil)))
+	}
+	grp := &Group{g: g, n: len(devices)}
+	runtime.SetFinalizer(grp, func(x *Group) { C.wva_group_destroy(x.g) })
+	return grp, nil
+}
+
+func (g *Group) err(rc C.int, what string) error {
+	if rc == C.WVA_OK {
+		return nil
+	}
+	return fmt.Errorf("%s: %d: %s", what, int(rc), C.GoString(C.wva_group_last_error(g.g)))
+}
+
+// Upload replicates the image on every device and shards the servers.  wva_group_upload takes the struct
+// form, so the slices are pinned for the duration of the call (runtime.Pinner, Go >= 1.21; the reference
+// is on go1.23, go.mod:7) -- the one place this binding builds a C struct of Go pointers.
+func (g *Group) Upload(img *SystemImage) error {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pf := func(s []float32) *C.float { if len(s) == 0 { return nil }; pin.Pin(&s[0]); return (*C.float)(unsafe.Pointer(&s[0])) }
+	pi := func(s []int32) *C.int32_t { if len(s) == 0 { return nil }; pin.Pin(&s[0]); return (*C.int32_t)(unsafe.Pointer(&s[0])) }
+	pl := func(s []int64) *C.int64_t { if len(s) == 0 { return nil }; pin.Pin(&s[0]); return (*C.int64_t)(unsafe.Pointer(&s[0])) }
+	pu := func(s []uint8) *C.uint8_t { if len(s) == 0 { return nil }; pin.Pin(&s[0]); return (*C.uint8_t)(unsafe.Pointer(&s[0])) }
+	h := (*C.wva_system_soa)(C.calloc(1, C.size_t(unsafe.Sizeof(C.wva_system_soa{}))))   // C memory: may hold pinned Go pointers
+	defer C.free(unsafe.Pointer(h))
+	h.n_servers, h.n_accels, h.n_models, h.n_types = C.int32_t(img.S), C.int32_t(img.A), C.int32_t(img.M), C.int32_t(img.T)
+	h.acc_cost, h.acc_multiplicity, h.acc_type, h.type_capacity = pf(img.AccCost), pi(img.AccMultiplicity), pi(img.AccType), pl(img.TypeCapacity)
+	h.perf_alpha, h.perf_beta, h.perf_gamma, h.perf_delta = pf(img.PerfAlpha), pf(img.PerfBeta), pf(img.PerfGamma), pf(img.PerfDelta)
+	h.perf_max_batch, h.perf_at_tokens, h.perf_acc_count, h.perf_valid = pi(img.PerfMaxBatch), pi(img.PerfAtTokens), pi(img.PerfAccCount), pu(img.PerfValid)
+	h.srv_model, h.srv_arrival_rpm, h.srv_in_tokens, h.srv_out_tokens = pi(img.SrvModel), pf(img.SrvArrivalRPM), pi(img.SrvInTokens), pi(img.SrvOutTokens)
+	h.srv_slo_ttft, h.srv_slo_itl, h.srv_slo_tps, h.srv_target_valid = pf(img.SrvSloTTFT), pf(img.SrvSloITL), pf(img.SrvSloTPS), pu(img.SrvTargetValid)
+	h.srv_priority, h.srv_min_replicas, h.srv_max_batch, h.srv_keep_acc = pi(img.SrvPriority), pi(img.SrvMinReplicas), pi(img.SrvMaxBatch), pu(img.SrvKeepAcc)
+	h.srv_cur_acc, h.srv_cur_replicas, h.srv_cur_cost = pi(img.SrvCurAcc), pi(img.SrvCurReplicas), pf(img.SrvCurCost)
+	return g.err(C.wva_group_upload(g.g, h), "wva_group_upload")
+}
+
+// Analyze: Server.Calculate for every pair (and the candidate sweep when rMax > 0) on all devices.
+func (g *Group) Analyze(rMax, bMax int) error {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	return g.err(C.wva_group_analyze(g.g, C.int32_t(rMax), C.int32_t(bMax), 0), "wva_group_analyze")
+}
+
+// AllocateByType: global per-type totals (NCCL all-gather of the partials inside the library).
+func (g *Group) AllocateByType(t int) ([]int64, []float32, error) {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	count, cost := make([]int64, t), make([]float32, t)
+	if t == 0 {
+		return count, cost, nil
+	}
+	return count, cost, g.err(C.wva_group_allocate_by_type(g.g, i64p(count), f32p(cost)), "wva_group_allocate_by_type")
 }

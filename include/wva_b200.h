@@ -184,6 +184,28 @@ int  wva_abi_version(void);
  * Uploads the image to HBM; invalidates previous analysis. */
 int wva_system_upload(wva_ctx* ctx, const wva_system_soa* host);
 
+/* cgo-callable forms.  cgo forbids passing a Go pointer to memory that itself holds Go pointers
+ * ("cgo argument has Go pointer to unpinned Go pointer"): a Go-allocated wva_system_soa / wva_alloc_soa
+ * whose fields point at Go slices cannot be passed as-is.  These variants take every array as its own
+ * argument -- each is a pointer to pointer-free memory, which cgo allows without pinning -- and are
+ * otherwise identical to wva_system_upload / wva_analyze_pairs / wva_pairs_fetch / wva_solve.  (The struct
+ * forms remain for C, C++ and ctypes callers, and for Go callers that pin with runtime.Pinner.) */
+int wva_system_upload_arrays(wva_ctx* ctx, int32_t n_servers, int32_t n_accels, int32_t n_models, int32_t n_types,
+        const float* acc_cost, const int32_t* acc_multiplicity, const int32_t* acc_type, const int64_t* type_capacity,
+        const float* perf_alpha, const float* perf_beta, const float* perf_gamma, const float* perf_delta,
+        const int32_t* perf_max_batch, const int32_t* perf_at_tokens, const int32_t* perf_acc_count, const uint8_t* perf_valid,
+        const int32_t* srv_model, const float* srv_arrival_rpm, const int32_t* srv_in_tokens, const int32_t* srv_out_tokens,
+        const float* srv_slo_ttft, const float* srv_slo_itl, const float* srv_slo_tps, const uint8_t* srv_target_valid,
+        const int32_t* srv_priority, const int32_t* srv_min_replicas, const int32_t* srv_max_batch, const uint8_t* srv_keep_acc,
+        const int32_t* srv_cur_acc, const int32_t* srv_cur_replicas, const float* srv_cur_cost);
+int wva_analyze_pairs_arrays(wva_ctx* ctx, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica, uint8_t* feasible);
+int wva_pairs_fetch_arrays(wva_ctx* ctx, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica, uint8_t* feasible);
+int wva_solve_arrays(wva_ctx* ctx, int32_t unlimited, int32_t delayed_best_effort, int32_t saturation_policy,
+        int32_t* chosen_acc, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica);
+
 /* Multi-GPU sharding: this rank owns servers [first, first+count) of the
  * uploaded image; analysis kernels touch only those; solve/allocate_by_type produce the
  * rank's partial results.  Default shard = everything. */
@@ -233,14 +255,16 @@ int wva_pairs_device(wva_ctx* ctx, wva_alloc_soa* dev, uint8_t** feasible);
  * process (cudaDeviceSynchronize), so the caller's collectives may run on any stream.  (With
  * wva_comm_init the library gathers the rows itself and none of this is needed.) */
 int wva_pairs_commit(wva_ctx* ctx);
-/* Tuning: certified closed-form tails on/off.  Chains that would run a long
- * constant-rate tail are first evaluated from the exact ramp plus the geometric closed form and accepted
- * only when every float32 rounding of the result is unambiguous within a proven error bound; otherwise
- * the exact chain runs.  Results are identical either way; default on (1).  With certified tails the
- * candidates of a (server, accelerator, replicas) row share one ramp across batch sizes when the
- * shard has >= 32 K rows (one thread per row); smaller shards use one thread per candidate.
- * on = 3: always one thread per candidate; on = 5: always one thread per row; on = 9: one warp per
- * row with lanes = batch sizes (tuning / A-B; all bit-identical). */
+/* Tuning: certified closed-form tails on/off and the sweep kernel.  Chains that
+ * would run a long constant-rate tail are first evaluated from the ramp plus the geometric closed form and
+ * accepted only when every float32 rounding of the result is unambiguous within a proven error bound;
+ * otherwise the exact chain runs.  Results are identical in every mode.
+ *   on = 1 (default): one WARP per (server, accelerator, replicas) row, lanes = 32 consecutive batch sizes,
+ *           the row's ramp built by warp scans (k_grid_scan);  on = 33: same, register allocation for 3 blocks/SM;
+ *   on = 0: no certificate, exact chains only (one thread per candidate);
+ *   on = 17: round-1 automatic choice: one thread per row (shared sequential ramp) for shards with >= 32 K rows,
+ *           one thread per candidate below;  on = 3 / 5 / 9: always one thread per candidate / one thread per
+ *           row / one warp per row with a lockstep ramp (tuning, A-B). */
 int wva_set_certified_tails(wva_ctx* ctx, int32_t on);
 /* Tuning: shards with at most max_pairs (server, accelerator) pairs use the warp-per-pair kernel
  * (speculative bisection, lowest latency); larger shards use one thread per pair (highest

@@ -23,6 +23,7 @@ EXPORTS = [
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
     "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
+    "wva_system_upload_arrays", "wva_analyze_pairs_arrays", "wva_pairs_fetch_arrays", "wva_solve_arrays",
     "wva_comm_unique_id", "wva_comm_init", "wva_comm_destroy", "wva_comm_info", "wva_comm_shard",
     "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx", "wva_group_last_error", "wva_group_upload",
     "wva_group_analyze", "wva_group_pairs_fetch", "wva_group_grid_fetch", "wva_group_solve", "wva_group_allocate_by_type",

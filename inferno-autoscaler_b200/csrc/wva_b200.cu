@@ -174,6 +174,7 @@ struct wva_ctx {
     int pairs_smem = 1;
     int certified = 1;
     int grid_rows = 1;
+    int grid_scan = 1;          // certified sweeps: 1 = warp-per-row scan kernel (default), 0 = the round-1 kernels; 2 = scan with 3 blocks/SM
     int pairs_debug = 0;
     DevBuf pairDbg;
 
@@ -347,7 +348,7 @@ int wva_ctx_create(int device, wva_ctx** out) {
     {
         const void* kernels[] = {(const void*)k_grid, (const void*)k_grid_rows, (const void*)k_grid_wrow, (const void*)k_grid_list,
                                  (const void*)k_grid_list_warp, (const void*)k_pairs_warp, (const void*)k_pairs, (const void*)k_grid_claim,
-                                 (const void*)k_grid_best_init};
+                                 (const void*)k_grid_best_init, (const void*)k_grid_scan<2>, (const void*)k_grid_scan<3>};
         if (!std::getenv("WVA_NO_CARVEOUT"))
             for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaGetLastError();
@@ -653,6 +654,9 @@ int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
     ctx->certified = (on & 1) ? 1 : 0;
     // bit 1: always one thread per candidate; bit 2: always one thread per row; bit 3: always one warp per row
     ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : ((on & 8) ? 3 : 1));
+    // bits 1-3 select one of the round-1 kernels explicitly (and switch the scan kernel off); bit 4 (16): round-1
+    // automatic choice (k_grid / k_grid_rows by shard size); bit 5 (32): scan kernel tuned for 3 blocks per SM
+    ctx->grid_scan = ((on & (2 | 4 | 8 | 16)) || !(on & 1)) ? 0 : ((on & 32) ? 2 : 1);
     ctx->dsys.cert = ctx->certified;
     return WVA_OK;
 }
@@ -785,23 +789,37 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     // certificate is ambiguous -- the exact chain of one b = 512 candidate is 11 264 dependent steps -- against
     // 0.55 ms for the per-candidate kernel, which finishes such chains inline while other warps work; so
     // segmentation is used only when asked for)
-    const bool rowsMode = ctx->certified && ctx->grid_rows && ctx->grid_rows != 3 &&
+    const bool scanMode = ctx->certified && ctx->grid_scan != 0;
+    const bool rowsMode = !scanMode && ctx->certified && ctx->grid_rows && ctx->grid_rows != 3 &&
                           (ctx->grid_rows == 2 || slicePairsMax * (size_t)r_max >= 32768);
     if (!(rowsMode && ctx->grid_rows == 2)) { gp.n_bseg = 1; gp.b_seg = b_max; }
     // one warp per row (k_grid_wrow), 8 rows per block: only when asked for.  Measured on config 2 (8 192 rows):
     // 0.33 ms for the rows + 0.38 ms for the 356 candidates whose certificate is ambiguous (k_grid_list_warp;
     // the phase lasts as long as its slowest exact chain) against 0.67 ms for k_grid on the same box, which
     // runs those chains inline while other warps work.
-    const bool wrowMode = ctx->certified && !rowsMode && ctx->grid_rows == 3 &&
+    const bool wrowMode = !scanMode && ctx->certified && !rowsMode && ctx->grid_rows == 3 &&
                           (size_t)b_max * 20 + 16 + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8 <= 200 * 1024;
     if (wrowMode) {
         gp.r_chunk = WVA_GRID_THREADS / 32;
+        gp.n_rchunks = (r_max + gp.r_chunk - 1) / gp.r_chunk;
+    }
+    if (scanMode) {
+        // one warp per row, 8 warps per block: a pair's rows are split over blocks only while the shard has fewer
+        // than ~4 blocks per SM of them (each block rebuilds the pair's 10 KB table)
+        int chunks = 1;
+        if (slicePairsMax > 0 && slicePairsMax < 592) chunks = (int)((592 + slicePairsMax - 1) / slicePairsMax);
+        const int maxChunks = (r_max + WVA_SCAN_WARPS - 1) / WVA_SCAN_WARPS;
+        if (chunks > maxChunks) chunks = maxChunks;
+        gp.r_chunk = (r_max + chunks - 1) / chunks;
+        gp.r_chunk = (gp.r_chunk + WVA_SCAN_WARPS - 1) / WVA_SCAN_WARPS * WVA_SCAN_WARPS;
         gp.n_rchunks = (r_max + gp.r_chunk - 1) / gp.r_chunk;
     }
     const size_t smem = (size_t)b_max * 20;
     if (smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_grid_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_grid_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // k_grid_wrow: the table, then per warp the checkpoints and the quotient buffer of warp_exact
     const size_t smemW = align_up(smem, 16) + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8;
@@ -839,7 +857,9 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
             CK(cudaEventRecord(ctx->evk0, ctx->gstream));
-            if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
+            if (scanMode && ctx->grid_scan == 2) k_grid_scan<3><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+            else if (scanMode) k_grid_scan<2><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+            else if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);
             else k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             LAUNCH_CHECK();
@@ -1576,6 +1596,62 @@ int wva_group_solve(wva_group* g, const wva_optimizer_spec* spec, int32_t* chose
 int wva_group_allocate_by_type(wva_group* g, int64_t* count, float* cost) {
     if (!g) return WVA_EINVAL;
     return g->each([&](int i, wva_ctx* c) { return wva_allocate_by_type(c, i == 0 ? count : nullptr, i == 0 ? cost : nullptr); });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// cgo-callable forms: every array its own argument (no pointer-to-pointer crosses the boundary)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int wva_system_upload_arrays(wva_ctx* ctx, int32_t n_servers, int32_t n_accels, int32_t n_models, int32_t n_types,
+        const float* acc_cost, const int32_t* acc_multiplicity, const int32_t* acc_type, const int64_t* type_capacity,
+        const float* perf_alpha, const float* perf_beta, const float* perf_gamma, const float* perf_delta,
+        const int32_t* perf_max_batch, const int32_t* perf_at_tokens, const int32_t* perf_acc_count, const uint8_t* perf_valid,
+        const int32_t* srv_model, const float* srv_arrival_rpm, const int32_t* srv_in_tokens, const int32_t* srv_out_tokens,
+        const float* srv_slo_ttft, const float* srv_slo_itl, const float* srv_slo_tps, const uint8_t* srv_target_valid,
+        const int32_t* srv_priority, const int32_t* srv_min_replicas, const int32_t* srv_max_batch, const uint8_t* srv_keep_acc,
+        const int32_t* srv_cur_acc, const int32_t* srv_cur_replicas, const float* srv_cur_cost) {
+    wva_system_soa h;
+    h.n_servers = n_servers; h.n_accels = n_accels; h.n_models = n_models; h.n_types = n_types;
+    h.acc_cost = acc_cost; h.acc_multiplicity = acc_multiplicity; h.acc_type = acc_type; h.type_capacity = type_capacity;
+    h.perf_alpha = perf_alpha; h.perf_beta = perf_beta; h.perf_gamma = perf_gamma; h.perf_delta = perf_delta;
+    h.perf_max_batch = perf_max_batch; h.perf_at_tokens = perf_at_tokens; h.perf_acc_count = perf_acc_count; h.perf_valid = perf_valid;
+    h.srv_model = srv_model; h.srv_arrival_rpm = srv_arrival_rpm; h.srv_in_tokens = srv_in_tokens; h.srv_out_tokens = srv_out_tokens;
+    h.srv_slo_ttft = srv_slo_ttft; h.srv_slo_itl = srv_slo_itl; h.srv_slo_tps = srv_slo_tps; h.srv_target_valid = srv_target_valid;
+    h.srv_priority = srv_priority; h.srv_min_replicas = srv_min_replicas; h.srv_max_batch = srv_max_batch; h.srv_keep_acc = srv_keep_acc;
+    h.srv_cur_acc = srv_cur_acc; h.srv_cur_replicas = srv_cur_replicas; h.srv_cur_cost = srv_cur_cost;
+    return wva_system_upload(ctx, &h);
+}
+
+static wva_alloc_soa make_alloc_soa(int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value, float* itl,
+                                    float* ttft, float* rho, float* max_arrv) {
+    wva_alloc_soa o;
+    o.acc = acc; o.num_replicas = num_replicas; o.batch_size = batch_size; o.cost = cost; o.value = value; o.itl = itl;
+    o.ttft = ttft; o.rho = rho; o.max_arrv_rate_per_replica = max_arrv;
+    return o;
+}
+
+int wva_analyze_pairs_arrays(wva_ctx* ctx, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica, uint8_t* feasible) {
+    wva_alloc_soa o = make_alloc_soa(acc, num_replicas, batch_size, cost, value, itl, ttft, rho, max_arrv_rate_per_replica);
+    return wva_analyze_pairs(ctx, &o, feasible);
+}
+
+int wva_pairs_fetch_arrays(wva_ctx* ctx, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica, uint8_t* feasible) {
+    wva_alloc_soa o = make_alloc_soa(acc, num_replicas, batch_size, cost, value, itl, ttft, rho, max_arrv_rate_per_replica);
+    return wva_pairs_fetch(ctx, &o, feasible);
+}
+
+int wva_solve_arrays(wva_ctx* ctx, int32_t unlimited, int32_t delayed_best_effort, int32_t saturation_policy,
+        int32_t* chosen_acc, int32_t* acc, int64_t* num_replicas, int64_t* batch_size, float* cost, float* value,
+        float* itl, float* ttft, float* rho, float* max_arrv_rate_per_replica) {
+    wva_optimizer_spec spec;
+    spec.unlimited = unlimited; spec.delayed_best_effort = delayed_best_effort; spec.saturation_policy = saturation_policy;
+    wva_alloc_soa o = make_alloc_soa(acc, num_replicas, batch_size, cost, value, itl, ttft, rho, max_arrv_rate_per_replica);
+    return wva_solve(ctx, &spec, chosen_acc, &o);
 }
 
 }  // extern "C"

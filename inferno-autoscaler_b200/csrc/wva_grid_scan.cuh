@@ -1,0 +1,312 @@
+// wva_grid_scan.cuh — the candidate sweep with ONE WARP PER ROW and a PARALLEL ramp (k_grid_scan).
+//
+// A row is (server, accelerator, replicas): all its candidates share lambda, and the chain of batch size
+// b is a prefix of the chain of b+1, so one ramp p[1..B] serves the whole row (as in k_grid_rows).  Here the
+// 32 lanes of a warp hold 32 CONSECUTIVE batch sizes of the same row:
+//
+//   * the ramp is not stepped sequentially: lane l forms the ratio lambda/s[n] of its own state and the warp
+//     builds p[n] = prod ratio, sum_{i<=n} p[i] and sum_{i<=n} i p[i] with three inclusive scans (5 shuffle
+//     steps each) plus a carry from the previous 32 states.  ~20 FP64 instructions per lane and chunk
+//     instead of 32 dependent ramp steps;
+//   * every lane then evaluates its own candidate from (p[b], sum, sum i p) with the certified closed-form
+//     tail (cert_eval_fast: two reciprocals instead of eight IEEE divisions);
+//   * the 32 results of a chunk are 1 KB of contiguous cube: one fully coalesced store per float4 half
+//     (k_grid_rows writes 32 B per lane at a 16 KB stride);
+//   * lanes of a warp share the replica count, so the "rate > RateRange.Max" early-outs and the died-out
+//     tail are (nearly) warp-uniform.
+//
+// Exactness.  The scans reassociate the ramp, so the ramp values are NOT bit-identical to the reference's
+// sequential p[n] (those of k_grid_rows are).  They do not have to be: the certificate
+// never used bit-identity of the ramp, only a bound on the distance between the quantities we feed into the
+// float32 roundings and their exact-arithmetic values.  Error budget of this kernel, in units of u = 2^-53,
+// relative, for candidate b (N = b, K = 11 b):
+//     ratio_i = lambda * rcp(s_i)                 <= 2 u     (rcp_refined is within 1 ulp of 1/s_i)
+//     p[n]   = product of n ratios, n-1 roundings <= 3 n u
+//     sums   : positive terms, scan depth 5 + one carry addition per chunk <= (5 + n/32 + 1) u on top
+//     tail   : closed forms with two reciprocals  <= 128 u   (see cert_eval_fast)
+// i.e. <= (3.1 N + 140) u <= 0.3 K u + 140 u on every aggregate, against the reference's own <= 8 K u distance
+// from exact arithmetic.  The acceptance test uses E = 64 K u >= 8 K u + 0.3 K u + 140 u for every K >= 3
+// (K >= 11 here), so an accepted float32 is the reference's float32; an ambiguous one goes to the exact-chain
+// kernels exactly as before.  The parity tests compare the ENTIRE config-2 cube and >= 1e6 candidates of
+// configs 3-5 (+ every deferred candidate, + exhaustive winner proofs) with the oracle.
+//
+// A lane whose p leaves the value window [2^-800, 2^990) on the high side (or is NaN) makes the rest of the
+// row "broken": those candidates go to the exact-chain kernels.  Leaving it on the low side with the ratio
+// already <= 0.998 (tame table: ratios do not grow again) means the chain has died out: p := 0, which is
+// within the budget above since sum >= 1.
+#pragma once
+
+namespace wva {
+
+// 1/x for a positive normal x well inside the exponent range: MUFU seed + two Newton steps (<= 1 ulp)
+__device__ __forceinline__ double rcp_pos(double x) { return rcp_refined(x); }
+
+// The certificate of cert_eval with the divisions folded into two reciprocals.  yTail = rcp_refined(sTail).
+// Own error (relative, units of u): oneR, r <= 2; inv <= 4; T0 <= 7, T1 <= 11 (+ the exp/log1p term of cert_eval when
+// x < 140: <= 80 on 1 - r^M (1 + x)); S, U <= 100; invS <= 102; every aggregate <= 128.
+__device__ __forceinline__ bool cert_eval_fast(const double pN, const double sumRamp, const double uN, const double lam,
+                                               const double sTail, const double yTail, const int N, const int K,
+                                               const float lambda, SolveStats& o) {
+    const int M = K - N;
+    if (M < 1 || K > (1 << 20)) return false;
+    const double oneR = (sTail - lam) * yTail;                 // 1 - r: exact subtraction of two float32 values
+    if (!(oneR >= 0x1p-11) || !(oneR < 1.0)) return false;      // r in (0, 0.9995]
+    const double r = lam * yTail;
+    const double x = (double)M * oneR;
+    if (!(x >= 0.3)) return false;
+    const double inv = rcp_pos(oneR);
+    double T0 = r * inv;
+    double T1 = T0 * inv;
+    double rM = 0.0;
+    if (x < 140.0) {                                            // r^M <= exp(-x): below 2^-200 it cannot matter
+        rM = exp((double)M * log1p(-oneR));
+        T0 = T0 * (1.0 - rM);
+        T1 = T1 * (1.0 - rM * (1.0 + x));
+    }
+    const double pT0 = pN * T0;
+    const double S = sumRamp + pT0;
+    const double U = uN + (pN * T1 + (double)N * pT0);
+    if (!(S < 0x1p1000) || !(U < 0x1p1000) || !(S > 0x1p-1000)) return false;
+    const double invS = rcp_pos(S);
+    const double tailMass = pT0 * invS;                          // 1 - sumP at i = N, without cancellation
+    const double pK = (pN * rM) * invS;
+    const double inSys = U * invS;
+    const double inServ = uN * invS + tailMass * (double)N;
+    const double Ku = (double)K * 0x1p-53;
+    const double E = 64.0 * Ku;
+    float inSysF, inServF, pKlo;
+    if (!same_f32(inSys, E * inSys, inSysF)) return false;
+    if (!same_f32(inServ, E * inServ + 4.0 * Ku * (double)N, inServF)) return false;
+    if (!same_f32(pK, 2.0 * E * pK, pKlo)) {
+        const float a = 1.0f - (float)(pK * (1.0 - 2.0 * E)), b = 1.0f - (float)(pK * (1.0 + 2.0 * E));
+        if (a != b) return false;
+        finish_stats_f32(o, lambda, inServF, inSysF, a);
+    } else {
+        finish_stats_f32(o, lambda, inServF, inSysF, 1.0f - pKlo);
+    }
+    o.rho = 0.0f;     // model.rho only feeds the stale-rho validity test, vacuous for K >= 2
+    return true;
+}
+
+__device__ __forceinline__ double shfl_up_d(double v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+
+// MINB = resident blocks per SM the register allocation is tuned for (2: 128 registers, no spills;
+// 3: 80 registers with spills) -- both instantiated, chosen at run time (wva_set_certified_tails).
+#define WVA_SCAN_WARPS 8
+template <int MINB>
+__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, MINB)
+k_grid_scan(DevSystem sys, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* rateD = reinterpret_cast<double*>(smem_raw);
+    double* rcp = rateD + gp.b_max;
+    float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
+    __shared__ int sh_nGood;
+    __shared__ unsigned long long sh_key;
+    __shared__ unsigned long long sh_cnt[3];
+
+    // block = (pair, chunk of replica counts): small shards split a pair's rows over n_rchunks blocks
+    const int pairSlice = blockIdx.x / gp.n_rchunks, rchunk = blockIdx.x % gp.n_rchunks;
+    const int rBeg = rchunk * gp.r_chunk + 1;
+    const int rEnd = (rBeg + gp.r_chunk - 1 < gp.r_max) ? rBeg + gp.r_chunk - 1 : gp.r_max;
+    const int pairLocal = gp.pair_base + pairSlice;
+    const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
+    const int s = gp.s0 + sl;
+    const int B = gp.b_max, R = gp.r_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
+        gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
+    }
+    const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
+    GridServer gs;
+    int blockStatus = WVA_CAND_OK;
+    if (!pairOk) blockStatus = WVA_CAND_ERR_PAIR;
+    else {
+        load_grid_server(sys, s, a, gs);
+        if (gs.inTok < 0 || gs.outTok < 1 || gs.sloTTFT < 0.0f || gs.sloITL < 0.0f || gs.sloTPS < 0.0f)
+            blockStatus = WVA_CAND_ERR_CONFIG;
+    }
+    const size_t candBase = ((size_t)pairLocal * R) * (size_t)B;
+    if (blockStatus != WVA_CAND_OK) {
+        const size_t n = (size_t)(rEnd - rBeg + 1) * B, off = (size_t)(rBeg - 1) * B;
+        if (gp.cube) {
+            float4* c = reinterpret_cast<float4*>(&gp.cube[candBase + off]);
+            const float4 z = make_float4(0, 0, 0, 0);
+            for (size_t j = threadIdx.x; j < 2 * n; j += blockDim.x) c[j] = z;
+        }
+        if (gp.status) for (size_t j = threadIdx.x; j < n; j += blockDim.x) gp.status[candBase + off + j] = (unsigned char)blockStatus;
+        return;
+    }
+    __syncthreads();
+    ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
+    double2* gtab = gp.pair_tab + (size_t)pairSlice * B;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float rt = sf.rate(i + 1);
+        rateF[i] = rt;
+        const double d = (double)rt;
+        const double y = rcp_refined(d);
+        rateD[i] = d; rcp[i] = y;
+        if (rchunk == 0) gtab[i] = make_double2(d, y);          // the exact-chain kernels read the table back
+        if (!(rt > 0.0f) || !(rt < CUDART_INF_F)) atomicMin(&sh_nGood, i);
+    }
+    const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
+    __syncthreads();
+    const int nGood = sh_nGood;
+
+    unsigned long long bestKey = WVA_KEY_NONE;
+    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    unsigned long long steps = 0, algSteps = 0, okCount = 0;
+
+    for (int r = rBeg + warp; r <= rEnd; r += WVA_SCAN_WARPS) {
+        const float rate = gs.totalRate / (float)r;
+        const float lambda = rate / 1000.0f;
+        const double lam = (double)lambda;
+        const bool lamOk = (lam >= 0x1p-100 && lam <= 0x1p20);
+        const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
+        value = value + 0.0f;
+        const size_t rowBase = candBase + (size_t)(r - 1) * B;
+        // carries of the three scans: state 0 is p = 1, sum = 1, sum i p = 0
+        double carryP = 1.0, carrySum = 1.0, carryU = 0.0;
+        bool rowBroken = !lamOk;       // every later candidate of the row needs the exact chain
+        for (int c0 = 0; c0 < B; c0 += 32) {
+            const int n = c0 + lane, b = n + 1;
+            const bool inRow = n < B;
+            const bool tabOk = inRow && b <= nGood;
+            // ---- ramp states c0+1 .. c0+32 by scans -------------------------------------------------
+            double P = tabOk ? lam * rcp[n] : 1.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(P, o); if (lane >= o) P *= t; }
+            double p = carryP * P;
+            const unsigned hq = (unsigned)__double2hiint(p);
+            bool laneBroken = false;
+            if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) {
+                // below the window (including 0 and subnormals) after the ratios have dropped under 0.998: died out
+                const bool died = tabOk && (p >= 0.0) && (p < 0x1p-800) && tame && (lambda <= 0.998f * rateF[n]);
+                if (died) p = 0.0; else laneBroken = true;
+            }
+            // a broken lane poisons every later state of the row
+            const unsigned brk = __ballot_sync(0xffffffffu, laneBroken && inRow);
+            const int firstBrk = brk ? (__ffs(brk) - 1) : 32;
+            const bool broken = rowBroken || lane >= firstBrk || !tabOk;
+            const double pUse = (lane < firstBrk && tabOk) ? p : 0.0;
+            double Ssum = pUse;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(Ssum, o); if (lane >= o) Ssum += t; }
+            const double sum = carrySum + Ssum;
+            double Us = (double)b * pUse;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(Us, o); if (lane >= o) Us += t; }
+            const double uN = carryU + Us;
+            carryP = __shfl_sync(0xffffffffu, p, 31);
+            carrySum = __shfl_sync(0xffffffffu, sum, 31);
+            carryU = __shfl_sync(0xffffffffu, uN, 31);
+            if (brk) rowBroken = true;
+            steps += 1;
+            if (!inRow) continue;
+            // ---- candidate (r, b) ----------------------------------------------------------------------
+            const size_t ci = rowBase + (size_t)n;
+            const int K = 11 * b;
+            const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
+            const float rateMax = lambdaMax * 1000.0f;
+            int st = WVA_CAND_OK;
+            bool feasible = false, skipWrite = false;
+            wva_metrics m;
+            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+            if (b > nGood) {                                   // bad table entry: literal path decides
+                const int k = atomicAdd(gp.slow_count, 1);
+                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+                skipWrite = true;
+            } else if (rate <= 0.0f) st = WVA_CAND_ERR_RATE_LE0;
+            else if (rate > rateMax) st = WVA_CAND_ERR_RATE_MAX;
+            else if (lambda < 0.0f) st = WVA_CAND_ERR_MODEL;
+            else {
+                SolveStats so;
+                bool certified = false;
+                if (!broken) certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
+                bool haveMetrics = false;
+                if (!certified) {
+                    // exact chain in the list kernels; when that list is full, right here
+                    const int k = atomicAdd(gp.heavy_count, 1);
+                    if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)ci; gp.heavy_cost[k] = (float)K; skipWrite = true; }
+                    else {
+                        ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
+                        float rt, dc;
+                        const int st2 = analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
+                        if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)ci; skipWrite = true; }
+                        else { st = st2; haveMetrics = true; }
+                    }
+                }
+                if (!skipWrite) {
+                    if (!haveMetrics) {
+                        const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+                        float rho = so.avgNumInServers / (float)b;
+                        rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+                        m.throughput = so.throughput * 1000.0f;
+                        m.avg_resp_time = so.avgRespTime;
+                        m.avg_wait_time = so.avgWaitTime;
+                        m.avg_num_in_serv = so.avgNumInServers;
+                        m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
+                        m.avg_token_time = decode_time(gs.sp, effConc);
+                        m.max_rate = rateMax;
+                        m.rho = rho;
+                    }
+                    if (st != WVA_CAND_OK) {
+                        m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+                        m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
+                    } else {
+                        okCount++;
+                        algSteps += 2ULL * (unsigned long long)(K + 1);
+                        const float lamMaxBack = rateMax / 1000.0f;
+                        const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+                        const float ttft = m.avg_wait_time + m.avg_prefill_time;
+                        const float itl = m.avg_token_time;
+                        feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
+                                   (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && (r >= gs.minReplicas);
+                        if (feasible && value == value) {              // a NaN value is never selected
+                            const unsigned long long key = make_key(value, a, r, b);
+                            if (key < bestKey) { bestKey = key; bestItl = itl; bestTtft = ttft; bestRho = m.rho; }
+                        }
+                    }
+                }
+            }
+            if (!skipWrite) {
+                if (gp.cube) {
+                    float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                    c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                    c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+                }
+                if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+            }
+        }
+    }
+    // ---- block argmin + counters ------------------------------------------------------------------
+    unsigned long long warpKey = bestKey;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
+        if (other < warpKey) warpKey = other;
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
+        okCount += __shfl_down_sync(0xffffffffu, okCount, o);
+    }
+    if (lane == 0) {
+        if (warpKey != WVA_KEY_NONE) atomicMin(&sh_key, warpKey);
+        atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
+    }
+    __syncthreads();
+    const unsigned long long blockKey = sh_key;
+    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {
+        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
+        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
+        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        gp.block_slot[blockIdx.x] = sl_;
+        atomicMin(&gp.keys[sl], blockKey);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
+    }
+}
+
+}  // namespace wva

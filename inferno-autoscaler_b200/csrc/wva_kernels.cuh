@@ -2701,3 +2701,5 @@ __global__ void k_greedy_collect(DevSystem sys, DevAllocs pairs, const int* __re
 }
 
 }  // namespace wva
+
+#include "wva_grid_scan.cuh"
