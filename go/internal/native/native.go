@@ -264,6 +264,22 @@ func (c *Context) QueueAnalyze(cfg []QueueConfig, rate []float32) ([]Metrics, []
 	return m, st, c.err(rc, "wva_queue_analyze")
 }
 
+// ModelSolve: a sequence of MM1ModelStateDependent.Solve(lambda[i], mu[i]) calls on one model
+// NewMM1ModelStateDependent(K, servRate); out has 9 floats per call {isValid, rho, avgRespTime, avgWaitTime,
+// avgServTime, avgNumInSystem, avgQueueLength, avgNumInServers, throughput}; p = probabilities after the last call.
+func (c *Context) ModelSolve(K int, servRate, lambda, mu []float32) (out []float32, p []float64, err error) {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	n := len(lambda)
+	out, p = make([]float32, 9*n), make([]float64, K+1)
+	if n == 0 || len(servRate) == 0 || len(mu) != n {
+		return out, p, fmt.Errorf("bad ModelSolve arguments")
+	}
+	rc := C.wva_model_solve(c.ctx, C.int64_t(K), f32p(servRate), C.int32_t(len(servRate)), C.int32_t(n), f32p(lambda), f32p(mu),
+		f32p(out), (*C.double)(unsafe.Pointer(&p[0])))
+	return out, p, c.err(rc, "wva_model_solve")
+}
+
 // QueueSize: n independent QueueAnalyzer.Size calls; target/rates/achieved are (TTFT, ITL, TPS) triples.
 func (c *Context) QueueSize(cfg []QueueConfig, target []float32) (rates []float32, m []Metrics, achieved []float32, status []uint8, err error) {
 	c.mu.Lock()

@@ -13,19 +13,12 @@ import (
 type Solver struct {
 	optimizerSpec     *config.OptimizerSpec
 	currentAllocation map[string]*core.Allocation
-	diffAllocation    map[string]*AllocationDiff
+	diffAllocation    map[string]*core.AllocationDiff
 	solutionTimeUsec  int64
 }
 
-// AllocationDiff mirrors core.AllocationDiff of the reference (allocation.go:338-379).
-type AllocationDiff struct {
-	OldAccelerator, NewAccelerator string
-	OldNumReplicas, NewNumReplicas int
-	CostDiff                       float32
-}
-
 func NewSolver(spec *config.OptimizerSpec) *Solver {
-	return &Solver{optimizerSpec: spec, currentAllocation: map[string]*core.Allocation{}, diffAllocation: map[string]*AllocationDiff{}}
+	return &Solver{optimizerSpec: spec, currentAllocation: map[string]*core.Allocation{}, diffAllocation: map[string]*core.AllocationDiff{}}
 }
 
 // Solve (solver.go:32-60)
@@ -41,22 +34,12 @@ func (s *Solver) Solve() error {
 		return err
 	}
 	s.solutionTimeUsec = usec
-	s.diffAllocation = map[string]*AllocationDiff{}
+	// solver.go:46-57: diff of current vs desired allocation per server
+	s.diffAllocation = map[string]*core.AllocationDiff{}
 	for name, server := range core.GetServers() {
-		cur, des := s.currentAllocation[name], server.Allocation()
-		if cur == nil && des == nil {
-			continue
+		if d := core.CreateAllocationDiff(s.currentAllocation[name], server.Allocation()); d != nil {
+			s.diffAllocation[name] = d
 		}
-		d := &AllocationDiff{OldAccelerator: "none", NewAccelerator: "none"}
-		var oldCost, newCost float32
-		if cur != nil {
-			d.OldAccelerator, d.OldNumReplicas, oldCost = cur.Accelerator(), cur.NumReplicas(), cur.Cost()
-		}
-		if des != nil {
-			d.NewAccelerator, d.NewNumReplicas, newCost = des.Accelerator(), des.NumReplicas(), des.Cost()
-		}
-		d.CostDiff = newCost - oldCost
-		s.diffAllocation[name] = d
 	}
 	return nil
 }
@@ -64,7 +47,8 @@ func (s *Solver) Solve() error {
 // SolveUnlimited / SolveGreedy keep the reference's entry points (solver.go:63, greedy.go:35).
 func (s *Solver) SolveUnlimited() { spec := *s.optimizerSpec; spec.Unlimited = true; _, _ = core.TheSystem.Solve(&spec) }
 func (s *Solver) SolveGreedy()    { spec := *s.optimizerSpec; spec.Unlimited = false; _, _ = core.TheSystem.Solve(&spec) }
-func (s *Solver) AllocationDiff() map[string]*AllocationDiff { return s.diffAllocation }
+// AllocationDiff (solver.go:81): the reference's return type.
+func (s *Solver) AllocationDiff() map[string]*core.AllocationDiff { return s.diffAllocation }
 
 type Optimizer struct {
 	spec             *config.OptimizerSpec

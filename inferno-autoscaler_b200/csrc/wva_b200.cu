@@ -810,6 +810,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         if (slicePairsMax > 0 && slicePairsMax < 592) chunks = (int)((592 + slicePairsMax - 1) / slicePairsMax);
         const int maxChunks = (r_max + WVA_SCAN_WARPS - 1) / WVA_SCAN_WARPS;
         if (chunks > maxChunks) chunks = maxChunks;
+        const int minChunks = (r_max + WVA_SCAN_MAXROWS - 1) / WVA_SCAN_MAXROWS;     // a block holds the exact-stop records of <= 64 rows
+        if (chunks < minChunks) chunks = minChunks;
         gp.r_chunk = (r_max + chunks - 1) / chunks;
         gp.r_chunk = (gp.r_chunk + WVA_SCAN_WARPS - 1) / WVA_SCAN_WARPS * WVA_SCAN_WARPS;
         gp.n_rchunks = (r_max + gp.r_chunk - 1) / gp.r_chunk;

@@ -90,9 +90,59 @@ __device__ __forceinline__ bool cert_eval_fast(const double pN, const double sum
 
 __device__ __forceinline__ double shfl_up_d(double v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
 
-// MINB = resident blocks per SM the register allocation is tuned for (2: 128 registers, no spills;
-// 3: 80 registers with spills) -- both instantiated, chosen at run time (wva_set_certified_tails).
+// Per-row result of the exact sequential ramp (phase A).  A lightly loaded row's chain dies out after a few
+// states; from there on the reference's sums no longer change and 1 - sumP is pure rounding noise of ITS
+// summation order, which no tolerance-based certificate can reproduce -- those candidates need the exact
+// sequential arithmetic (the "stopped" path of k_grid_rows, same rule, same code shape):
+//   stopB   first batch size whose candidates use the frozen exact sums (INT_MAX: the row never stops)
+//   brokenB first batch size from which the row must go to the exact-chain kernels (window exit in the exact ramp)
+struct ScanRow { int stopB, brokenB; double exInSys, exSumP; };
+
+// The exact ramp of one row up to its stop: the reference's recurrence, sequential, bit-identical
+// (mm1modelstatedependent.go:77-112), with solve_stream's truncation rule at a 2^10 stricter threshold.
+__device__ __forceinline__ void scan_row_exact(const double* rateD, const double* rcp, const float* rateF, const int B, const int nGood,
+                                               const bool tame, const float lambda, ScanRow& out, unsigned long long& steps) {
+    out.stopB = 0x7fffffff; out.brokenB = 0x7fffffff; out.exInSys = 0.0; out.exSumP = 0.0;
+    const double lam = (double)lambda;
+    if (!(lam >= 0x1p-100 && lam <= 0x1p20)) { out.brokenB = 1; return; }
+    // a row stops only after its ratios have dropped under 0.998: with a tame (non-decreasing) table that never
+    // happens when even the largest rate is too small
+    if (!tame || !(lambda <= 0.998f * rateF[(nGood < B ? nGood : B) - 1 < 0 ? 0 : (nGood < B ? nGood : B) - 1])) return;
+    double p = 1.0, sum = 1.0;
+    unsigned thrHi = 0u, hmin = 0x3ff00000u;
+    const int nEnd = nGood < B ? nGood : B;
+    for (int n = 0; n < nEnd; ++n) {
+        const double pn = div_core(p * lam, rateD[n], rcp[n]);
+        const unsigned hq = (unsigned)__double2hiint(pn);
+        if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) { out.brokenB = n + 1; break; }
+        sum += pn; p = pn;
+        ++steps;
+        if (n == 0 && pn >= 0x1p-400) thrHi = (unsigned)__double2hiint((0x1p-68 * fmin(1.0, pn)) / (double)(11 * B));
+        hmin = hq < hmin ? hq : hmin;
+        if (hq < thrHi && lambda <= 0.998f * rateF[n] && sum <= 0x1p400) {
+            const int b = n + 1;
+            const double S = sum;
+            if ((int)(hmin >> 20) - (int)((unsigned)__double2hiint(S) >> 20) < -1000) { out.brokenB = b; break; }
+            const double yS = rcp_refined(S);
+            double q = div_core(1.0, S, yS), pp = 1.0, di = 0.0, exSumP = q, exInSys = 0.0;
+            for (int i = 1; i <= b; ++i) {
+                pp = div_core(pp * lam, rateD[i - 1], rcp[i - 1]);
+                q = div_core(pp, S, yS);
+                di += 1.0;
+                exInSys += di * q;
+                exSumP += q;
+            }
+            steps += (unsigned long long)b;
+            out.stopB = b; out.exInSys = exInSys; out.exSumP = exSumP;
+            break;
+        }
+    }
+}
+
+// MINB = resident blocks per SM the register allocation is tuned for -- both instantiated, chosen at run time
+// (wva_set_certified_tails).
 #define WVA_SCAN_WARPS 8
+#define WVA_SCAN_MAXROWS 64        /* rows (replica counts) per block */
 template <int MINB>
 __global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, MINB)
 k_grid_scan(DevSystem sys, GridParams gp) {
@@ -103,6 +153,7 @@ k_grid_scan(DevSystem sys, GridParams gp) {
     __shared__ int sh_nGood;
     __shared__ unsigned long long sh_key;
     __shared__ unsigned long long sh_cnt[3];
+    __shared__ ScanRow sh_row[WVA_SCAN_MAXROWS];
 
     // block = (pair, chunk of replica counts): small shards split a pair's rows over n_rchunks blocks
     const int pairSlice = blockIdx.x / gp.n_rchunks, rchunk = blockIdx.x % gp.n_rchunks;
@@ -154,59 +205,77 @@ k_grid_scan(DevSystem sys, GridParams gp) {
     __syncthreads();
     const int nGood = sh_nGood;
 
+    unsigned long long steps = 0, algSteps = 0, okCount = 0;
+    // ---- phase A: one thread per row runs the exact ramp to the row's stop --------------------------------------
+    for (int rr = threadIdx.x; rr <= rEnd - rBeg; rr += blockDim.x) {
+        const float lambdaA = (gs.totalRate / (float)(rBeg + rr)) / 1000.0f;
+        ScanRow row;
+        scan_row_exact(rateD, rcp, rateF, B, nGood, tame, lambdaA, row, steps);
+        sh_row[rr] = row;
+    }
+    __syncthreads();
+
+    // ---- phase B: one warp per row, lanes = 32 consecutive batch sizes ---------------------------------------------
     unsigned long long bestKey = WVA_KEY_NONE;
     float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
-    unsigned long long steps = 0, algSteps = 0, okCount = 0;
-
     for (int r = rBeg + warp; r <= rEnd; r += WVA_SCAN_WARPS) {
         const float rate = gs.totalRate / (float)r;
         const float lambda = rate / 1000.0f;
         const double lam = (double)lambda;
-        const bool lamOk = (lam >= 0x1p-100 && lam <= 0x1p20);
         const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
         float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
         value = value + 0.0f;
+        const bool valueOk = value == value;                       // a NaN value is never selected
+        const unsigned long long rowKey = make_key(value, a, r, 1);
+        const bool rateOk = rate > 0.0f;                            // else every candidate of the row is ERR_RATE_LE0
+        const bool repOk = r >= gs.minReplicas;
+        const ScanRow row = sh_row[r - rBeg];
+        wva_metrics* const rowCube = gp.cube ? gp.cube + candBase + (size_t)(r - 1) * B : nullptr;
+        unsigned char* const rowStatus = gp.status ? gp.status + candBase + (size_t)(r - 1) * B : nullptr;
         const size_t rowBase = candBase + (size_t)(r - 1) * B;
         // carries of the three scans: state 0 is p = 1, sum = 1, sum i p = 0
         double carryP = 1.0, carrySum = 1.0, carryU = 0.0;
-        bool rowBroken = !lamOk;       // every later candidate of the row needs the exact chain
+        bool rowBroken = false;        // the scan ramp left the value window: later candidates need the exact chain
         for (int c0 = 0; c0 < B; c0 += 32) {
             const int n = c0 + lane, b = n + 1;
             const bool inRow = n < B;
             const bool tabOk = inRow && b <= nGood;
-            // ---- ramp states c0+1 .. c0+32 by scans -------------------------------------------------
-            double P = tabOk ? lam * rcp[n] : 1.0;
+            const bool stoppedLane = b >= row.stopB;
+            double p = 0.0, sum = 0.0, uN = 0.0;
+            bool broken = rowBroken || !tabOk || b >= row.brokenB;
+            if (c0 + 1 < row.stopB && c0 + 1 < row.brokenB && !rowBroken) {       // warp-uniform: some lane still needs the ramp
+                // ---- ramp states c0+1 .. c0+32 by scans --------------------------------------------------------
+                double P = tabOk ? lam * rcp[n] : 1.0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(P, o); if (lane >= o) P *= t; }
-            double p = carryP * P;
-            const unsigned hq = (unsigned)__double2hiint(p);
-            bool laneBroken = false;
-            if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) {
-                // below the window (including 0 and subnormals) after the ratios have dropped under 0.998: died out
-                const bool died = tabOk && (p >= 0.0) && (p < 0x1p-800) && tame && (lambda <= 0.998f * rateF[n]);
-                if (died) p = 0.0; else laneBroken = true;
+                for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(P, o); if (lane >= o) P *= t; }
+                p = carryP * P;
+                const unsigned hq = (unsigned)__double2hiint(p);
+                bool laneBroken = false;
+                if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) {
+                    // below the window (0 and subnormals included) after the ratios have dropped under 0.998: died out
+                    const bool died = tabOk && (p >= 0.0) && (p < 0x1p-800) && tame && (lambda <= 0.998f * rateF[n]);
+                    if (died) p = 0.0; else laneBroken = inRow;
+                }
+                const unsigned brk = __ballot_sync(0xffffffffu, laneBroken);
+                const int firstBrk = brk ? (__ffs(brk) - 1) : 32;
+                broken = broken || lane >= firstBrk;
+                const double pUse = (lane < firstBrk && tabOk) ? p : 0.0;
+                double Ssum = pUse, Us = (double)b * pUse;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t1 = shfl_up_d(Ssum, o), t2 = shfl_up_d(Us, o);
+                    if (lane >= o) { Ssum += t1; Us += t2; }
+                }
+                sum = carrySum + Ssum;
+                uN = carryU + Us;
+                carryP = __shfl_sync(0xffffffffu, p, 31);
+                carrySum = __shfl_sync(0xffffffffu, sum, 31);
+                carryU = __shfl_sync(0xffffffffu, uN, 31);
+                if (brk) rowBroken = true;
+                steps += 1;
             }
-            // a broken lane poisons every later state of the row
-            const unsigned brk = __ballot_sync(0xffffffffu, laneBroken && inRow);
-            const int firstBrk = brk ? (__ffs(brk) - 1) : 32;
-            const bool broken = rowBroken || lane >= firstBrk || !tabOk;
-            const double pUse = (lane < firstBrk && tabOk) ? p : 0.0;
-            double Ssum = pUse;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(Ssum, o); if (lane >= o) Ssum += t; }
-            const double sum = carrySum + Ssum;
-            double Us = (double)b * pUse;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(Us, o); if (lane >= o) Us += t; }
-            const double uN = carryU + Us;
-            carryP = __shfl_sync(0xffffffffu, p, 31);
-            carrySum = __shfl_sync(0xffffffffu, sum, 31);
-            carryU = __shfl_sync(0xffffffffu, uN, 31);
-            if (brk) rowBroken = true;
-            steps += 1;
             if (!inRow) continue;
             // ---- candidate (r, b) ----------------------------------------------------------------------
-            const size_t ci = rowBase + (size_t)n;
             const int K = 11 * b;
             const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
             const float rateMax = lambdaMax * 1000.0f;
@@ -217,30 +286,39 @@ k_grid_scan(DevSystem sys, GridParams gp) {
             m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
             if (b > nGood) {                                   // bad table entry: literal path decides
                 const int k = atomicAdd(gp.slow_count, 1);
-                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)(rowBase + n);
                 skipWrite = true;
-            } else if (rate <= 0.0f) st = WVA_CAND_ERR_RATE_LE0;
+            } else if (!rateOk) st = WVA_CAND_ERR_RATE_LE0;
             else if (rate > rateMax) st = WVA_CAND_ERR_RATE_MAX;
             else if (lambda < 0.0f) st = WVA_CAND_ERR_MODEL;
             else {
                 SolveStats so;
                 bool certified = false;
-                if (!broken) certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
+                if (!broken) {
+                    if (stoppedLane) {
+                        // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no
+                        // longer change; float32(p[K]) < 2^-58 so throughput == lambda
+                        const double inServ = row.exInSys + (1.0 - row.exSumP) * (double)b;
+                        finish_stats(so, lambda, inServ, row.exInSys, 0.0f);
+                        certified = true;
+                    } else certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
+                }
                 bool haveMetrics = false;
                 if (!certified) {
                     // exact chain in the list kernels; when that list is full, right here
                     const int k = atomicAdd(gp.heavy_count, 1);
-                    if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)ci; gp.heavy_cost[k] = (float)K; skipWrite = true; }
+                    if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)(rowBase + n); gp.heavy_cost[k] = (float)K; skipWrite = true; }
                     else {
                         ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
                         float rt, dc;
                         const int st2 = analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
-                        if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)ci; skipWrite = true; }
+                        if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); skipWrite = true; }
                         else { st = st2; haveMetrics = true; }
                     }
                 }
                 if (!skipWrite) {
                     if (!haveMetrics) {
+                        // EffectiveConcurrency (queueanalyzer.go:296-302) with the row-invariant parts hoisted by the compiler
                         const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
                         float rho = so.avgNumInServers / (float)b;
                         rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
@@ -264,21 +342,21 @@ k_grid_scan(DevSystem sys, GridParams gp) {
                         const float ttft = m.avg_wait_time + m.avg_prefill_time;
                         const float itl = m.avg_token_time;
                         feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
-                                   (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && (r >= gs.minReplicas);
-                        if (feasible && value == value) {              // a NaN value is never selected
-                            const unsigned long long key = make_key(value, a, r, b);
+                                   (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && repOk;
+                        if (feasible && valueOk) {
+                            const unsigned long long key = rowKey + (unsigned long long)(b - 1);
                             if (key < bestKey) { bestKey = key; bestItl = itl; bestTtft = ttft; bestRho = m.rho; }
                         }
                     }
                 }
             }
             if (!skipWrite) {
-                if (gp.cube) {
-                    float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+                if (rowCube) {
+                    float4* c = reinterpret_cast<float4*>(&rowCube[n]);
                     c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
                     c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
                 }
-                if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+                if (rowStatus) rowStatus[n] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
             }
         }
     }

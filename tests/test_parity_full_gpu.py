@@ -57,7 +57,7 @@ def _check_sweep_against_oracle(wva, oracle, ctx, img, first, count, R, B, n_ran
     ctx.set_shard(first, count)
     best, cube, status = ctx.analyze_grid(R, B, want_cube=True)
     lists = ctx.grid_list_sizes()
-    deferred, n_def = ctx.grid_deferred()
+    deferred, n_def = ctx.grid_deferred(cap=1 << 24)
     assert n_def == len(deferred) == lists["deferred"]
     ncand = count * A * R * B
     assert len(cube) == ncand

@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU pass 2: scan kernel v2 A/B, parity tests, bench, ncu
+set -x
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python tools/grid_ab.py 3 1 33 17 > gpurun_out/r02b_grid_ab_cfg3.txt 2>&1
+timeout 300 python tools/grid_ab.py 2 1 33 17 3 > gpurun_out/r02b_grid_ab_cfg2.txt 2>&1
+( time timeout 1800 python -m pytest tests -m gpu -x -q -s --durations=25 ) > gpurun_out/r02b_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r02b_pytest.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02b_bench_n1.json 2> gpurun_out/r02b_bench_n1.err
+( time timeout 900 python bench.py --impl reference --steps 3 --warmup 3 ) > gpurun_out/r02b_ref.json 2> gpurun_out/r02b_ref.err
+timeout 600 python tools/greedy_stats.py > gpurun_out/r02b_greedy_stats.txt 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02b_launches_cfg3.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_grid_scan -s 3 -c 1 -o gpurun_out/r02b_scan \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_ncu_scan.log 2>&1
+cp inferno-autoscaler_b200/libwva_b200.so gpurun_out/r02b_libwva_b200.so
+ls -la gpurun_out | tail -20
