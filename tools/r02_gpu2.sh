@@ -14,5 +14,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_grid_scan -s 3 -c 1 -o gpurun_out/r02b_scan \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_ncu_scan.log 2>&1
-cp inferno-autoscaler_b200/libwva_b200.so gpurun_out/r02b_libwva_b200.so
 ls -la gpurun_out | tail -20
