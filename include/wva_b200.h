@@ -184,6 +184,27 @@ int  wva_abi_version(void);
  * Uploads the image to HBM; invalidates previous analysis. */
 int wva_system_upload(wva_ctx* ctx, const wva_system_soa* host);
 
+/* Incremental updates of the RESIDENT image (System.AddServerFromSpec / RemoveServer / SetCountFromSpec /
+ * Model.AddPerfDataFromSpec, pkg/core/system.go:99-171, model.go:45-54): only the touched rows cross PCIe.
+ * wva_system_upload lays the arrays out with spare rows (1/16 more, at least 64); an update that would
+ * outgrow them fails with WVA_ECAPACITY and the caller uploads the whole image again.  Every update
+ * invalidates previous analysis results and resets the shard to "everything".
+ *   wva_system_update_servers: overwrite server rows [first, first+count) from rows->srv_* (arrays of
+ *       `count` entries; rows->n_servers == count); first + count may extend the image (first <= S);
+ *   wva_system_update_models:  overwrite the perf rows of models [first, first+count) from rows->perf_*
+ *       (count * A entries; rows->n_models == count); may extend M the same way;
+ *   wva_system_remove_server:  the last server's row moves into `index` (device-side), S shrinks by one --
+ *       the host keeps its name -> index map in step;
+ *   wva_system_set_capacity:   the T capacity counters.
+ * wva_upload_bytes: bytes the last upload / update call moved host -> device. */
+#define WVA_ECAPACITY  -6   /* the resident image has no spare row left: upload again */
+int wva_system_update_servers(wva_ctx* ctx, int32_t first, int32_t count, const wva_system_soa* rows);
+int wva_system_update_models(wva_ctx* ctx, int32_t first, int32_t count, const wva_system_soa* rows);
+int wva_system_remove_server(wva_ctx* ctx, int32_t index);
+int wva_system_set_capacity(wva_ctx* ctx, const int64_t* type_capacity);
+int64_t wva_upload_bytes(const wva_ctx* ctx);
+int wva_system_dims(const wva_ctx* ctx, int32_t* n_servers, int32_t* n_accels, int32_t* n_models, int32_t* n_types);
+
 /* cgo-callable forms.  cgo forbids passing a Go pointer to memory that itself holds Go pointers
  * ("cgo argument has Go pointer to unpinned Go pointer"): a Go-allocated wva_system_soa / wva_alloc_soa
  * whose fields point at Go slices cannot be passed as-is.  These variants take every array as its own

@@ -9,7 +9,7 @@ import numpy as np
 
 ABI_VERSION = 1
 
-OK, EINVAL, ECUDA, ESTATE, ENOSOLUTION, ENONFINITE = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ECUDA, ESTATE, ENOSOLUTION, ENONFINITE, ECAPACITY = 0, -1, -2, -3, -4, -5, -6
 
 POLICY_NONE, POLICY_PRIORITY_EXHAUSTIVE, POLICY_PRIORITY_ROUND_ROBIN, POLICY_ROUND_ROBIN = 0, 1, 2, 3
 POLICY_BY_NAME = {  # SaturatedAllocationPolicyEnum, reference pkg/config/config.go:28-41

@@ -24,6 +24,7 @@ EXPORTS = [
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
     "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
     "wva_system_upload_arrays", "wva_analyze_pairs_arrays", "wva_pairs_fetch_arrays", "wva_solve_arrays",
+    "wva_system_update_servers", "wva_system_update_models", "wva_system_remove_server", "wva_system_set_capacity", "wva_upload_bytes", "wva_system_dims",
     "wva_comm_unique_id", "wva_comm_init", "wva_comm_destroy", "wva_comm_info", "wva_comm_shard",
     "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx", "wva_group_last_error", "wva_group_upload",
     "wva_group_analyze", "wva_group_pairs_fetch", "wva_group_grid_fetch", "wva_group_solve", "wva_group_allocate_by_type",
@@ -89,6 +90,13 @@ def lib():
         L.wva_grid_deferred_fetch.argtypes = [vp, C.POINTER(u64), i32, C.POINTER(i32)]
         L.wva_stream.argtypes = [vp]
         L.wva_stream.restype = vp
+        L.wva_system_update_servers.argtypes = [vp, i32, i32, C.POINTER(abi.SystemSoa)]
+        L.wva_system_update_models.argtypes = [vp, i32, i32, C.POINTER(abi.SystemSoa)]
+        L.wva_system_remove_server.argtypes = [vp, i32]
+        L.wva_system_set_capacity.argtypes = [vp, abi.i64p]
+        L.wva_upload_bytes.argtypes = [vp]
+        L.wva_upload_bytes.restype = i64
+        L.wva_system_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.wva_comm_unique_id.argtypes = [vp]
         L.wva_comm_init.argtypes = [vp, vp, i32, i32]
         L.wva_comm_destroy.argtypes = [vp]
@@ -180,6 +188,60 @@ class Context:
         self._ck(lib().wva_system_upload(self._h, C.byref(s)))
         self.image = image
         self.first, self.count = 0, image.S
+
+    # ---- incremental updates of the resident image (system.go:99-171) ------------------------
+    def update_servers(self, first, rows: SystemImage):
+        """overwrite / append server rows [first, first+rows.S) from `rows` (its server arrays); self.image follows"""
+        s = rows.c_struct()
+        self._ck(lib().wva_system_update_servers(self._h, int(first), rows.S, C.byref(s)))
+        img = self.image
+        newS = max(img.S, first + rows.S)
+        for name, dt in abi.SRV_FIELDS:
+            arr = getattr(img, name)
+            if newS > img.S:
+                arr = np.concatenate([arr, np.zeros(newS - img.S, dtype=dt)])
+            arr[first:first + rows.S] = getattr(rows, name)
+            setattr(img, name, arr)
+        img.S = newS
+        self.first, self.count = 0, newS
+
+    def update_models(self, first, rows: SystemImage):
+        s = rows.c_struct()
+        self._ck(lib().wva_system_update_models(self._h, int(first), rows.M, C.byref(s)))
+        img = self.image
+        newM = max(img.M, first + rows.M)
+        for name, dt in abi.PERF_FIELDS:
+            arr = getattr(img, name)
+            if newM > img.M:
+                arr = np.concatenate([arr, np.zeros((newM - img.M) * img.A, dtype=dt)])
+            arr[first * img.A:(first + rows.M) * img.A] = getattr(rows, name)
+            setattr(img, name, arr)
+        img.M = newM
+        self.first, self.count = 0, img.S
+
+    def remove_server(self, index):
+        """RemoveServer: the last server's row moves into `index`; self.image follows"""
+        self._ck(lib().wva_system_remove_server(self._h, int(index)))
+        img = self.image
+        for name, _ in abi.SRV_FIELDS:
+            arr = getattr(img, name)
+            arr[index] = arr[img.S - 1]
+            setattr(img, name, arr[:img.S - 1].copy())
+        img.S -= 1
+        self.first, self.count = 0, img.S
+
+    def set_capacity(self, type_capacity):
+        cap = np.ascontiguousarray(type_capacity, dtype=np.int64)
+        self._ck(lib().wva_system_set_capacity(self._h, abi.ptr(cap, C.c_int64)))
+        self.image.type_capacity = cap.copy()
+
+    def upload_bytes(self):
+        return int(lib().wva_upload_bytes(self._h))
+
+    def dims(self):
+        v = [C.c_int32(0) for _ in range(4)]
+        self._ck(lib().wva_system_dims(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     def set_shard(self, first, count):
         self._ck(lib().wva_set_shard(self._h, int(first), int(count)))

@@ -157,7 +157,13 @@ struct wva_ctx {
     std::atomic<int64_t> launches{0};
     int64_t phase_usec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    // system image
+    // system image: arrays are laid out with spare rows (Scap servers, Mcap models) so that the incremental
+    // updates of pkg/core/system.go:99-171 touch only the rows that change (wva_system_update_*)
+    int Scap = 0, Mcap = 0;
+    size_t off_srv[15] = {0}, off_perf[8] = {0}, off_cap = 0;
+    int64_t last_h2d_bytes = 0;
+    std::vector<int32_t> h_srv_model, h_srv_out, h_srv_mb, h_pmb, h_pat;    // host copies that size the pair tables (hostN)
+    std::vector<float> h_srv_arr;
     bool have_system = false;
     DevSystem dsys{};
     DevBuf arena;
@@ -406,6 +412,31 @@ int64_t wva_phase_time_usec(const wva_ctx* ctx, int phase) {
 }
 int64_t wva_solution_time_usec(const wva_ctx* ctx) { return wva_phase_time_usec(ctx, WVA_PHASE_SOLVE); }
 
+// N of CreateAllocation (allocation.go:77-87) per pair of servers [s0, s1), or an upper bound where the device
+// finds the pair unusable (it then needs no table at all): sizes the tables of the warp-per-pair kernel
+// without a device round trip
+static void host_plan_rows(wva_ctx* ctx, int s0, int s1) {
+    const int A = ctx->A;
+    for (int s = s0; s < s1; ++s) {
+        const int m = ctx->h_srv_model[(size_t)s];
+        const long long outTok = ctx->h_srv_out[(size_t)s];
+        for (int a = 0; a < A; ++a) ctx->hostN[(size_t)s * A + a] = 0;
+        if (ctx->h_srv_arr[(size_t)s] == 0.0f || outTok == 0) continue;
+        for (int a = 0; a < A; ++a) {
+            long long n;
+            if (ctx->h_srv_mb[(size_t)s] > 0) n = ctx->h_srv_mb[(size_t)s];
+            else if (m < 0) n = 0;
+            else {
+                const size_t pi = (size_t)m * A + a;
+                const long long prod = (long long)((unsigned long long)(long long)ctx->h_pmb[pi] * (unsigned long long)(long long)ctx->h_pat[pi]);
+                n = (outTok == -1) ? (long long)(0ull - (unsigned long long)prod) : prod / outTok;
+                if (n < 1) n = 1;
+            }
+            ctx->hostN[(size_t)s * A + a] = n;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
     if (!ctx || !h) return fail(ctx, WVA_EINVAL, "null argument");
@@ -426,18 +457,29 @@ int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
     struct Item { const void* src; size_t bytes; size_t off; };
     std::vector<Item> items;
     size_t off = 0;
-    auto add = [&](const void* src, size_t bytes) { items.push_back({src, bytes, off}); size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t MA = (size_t)M * A;
-    size_t o_acc_cost = add(h->acc_cost, A * 4), o_acc_mult = add(h->acc_multiplicity, A * 4), o_acc_type = add(h->acc_type, A * 4);
-    size_t o_cap = add(h->type_capacity, (size_t)T * 8);
-    size_t o_pa = add(h->perf_alpha, MA * 4), o_pb = add(h->perf_beta, MA * 4), o_pg = add(h->perf_gamma, MA * 4), o_pd = add(h->perf_delta, MA * 4);
-    size_t o_pmb = add(h->perf_max_batch, MA * 4), o_pat = add(h->perf_at_tokens, MA * 4), o_pac = add(h->perf_acc_count, MA * 4), o_pv = add(h->perf_valid, MA);
-    size_t o_sm = add(h->srv_model, (size_t)S * 4), o_sar = add(h->srv_arrival_rpm, (size_t)S * 4), o_sin = add(h->srv_in_tokens, (size_t)S * 4),
-           o_sout = add(h->srv_out_tokens, (size_t)S * 4), o_stt = add(h->srv_slo_ttft, (size_t)S * 4), o_sit = add(h->srv_slo_itl, (size_t)S * 4),
-           o_stp = add(h->srv_slo_tps, (size_t)S * 4), o_stv = add(h->srv_target_valid, (size_t)S), o_spr = add(h->srv_priority, (size_t)S * 4),
-           o_smr = add(h->srv_min_replicas, (size_t)S * 4), o_smb = add(h->srv_max_batch, (size_t)S * 4), o_ska = add(h->srv_keep_acc, (size_t)S),
-           o_sca = add(h->srv_cur_acc, (size_t)S * 4), o_scr = add(h->srv_cur_replicas, (size_t)S * 4), o_scc = add(h->srv_cur_cost, (size_t)S * 4);
+    // spare rows for wva_system_update_servers / _models: 1/16 more, at least 64
+    const int Scap = S + (S / 16 > 64 ? S / 16 : 64), Mcap = M + (M / 16 > 64 ? M / 16 : 64);
+    auto add = [&](const void* src, size_t n, size_t cap, size_t elem) { items.push_back({src, n * elem, off}); size_t o = off; off = align_up(off + cap * elem, 256); return o; };
+    const size_t MA = (size_t)M * A, MAcap = (size_t)Mcap * A;
+    size_t o_acc_cost = add(h->acc_cost, A, A, 4), o_acc_mult = add(h->acc_multiplicity, A, A, 4), o_acc_type = add(h->acc_type, A, A, 4);
+    size_t o_cap = add(h->type_capacity, (size_t)T, (size_t)T, 8);
+    size_t o_pa = add(h->perf_alpha, MA, MAcap, 4), o_pb = add(h->perf_beta, MA, MAcap, 4), o_pg = add(h->perf_gamma, MA, MAcap, 4), o_pd = add(h->perf_delta, MA, MAcap, 4);
+    size_t o_pmb = add(h->perf_max_batch, MA, MAcap, 4), o_pat = add(h->perf_at_tokens, MA, MAcap, 4), o_pac = add(h->perf_acc_count, MA, MAcap, 4), o_pv = add(h->perf_valid, MA, MAcap, 1);
+    const size_t Sz = (size_t)S, Sc = (size_t)Scap;
+    size_t o_sm = add(h->srv_model, Sz, Sc, 4), o_sar = add(h->srv_arrival_rpm, Sz, Sc, 4), o_sin = add(h->srv_in_tokens, Sz, Sc, 4),
+           o_sout = add(h->srv_out_tokens, Sz, Sc, 4), o_stt = add(h->srv_slo_ttft, Sz, Sc, 4), o_sit = add(h->srv_slo_itl, Sz, Sc, 4),
+           o_stp = add(h->srv_slo_tps, Sz, Sc, 4), o_stv = add(h->srv_target_valid, Sz, Sc, 1), o_spr = add(h->srv_priority, Sz, Sc, 4),
+           o_smr = add(h->srv_min_replicas, Sz, Sc, 4), o_smb = add(h->srv_max_batch, Sz, Sc, 4), o_ska = add(h->srv_keep_acc, Sz, Sc, 1),
+           o_sca = add(h->srv_cur_acc, Sz, Sc, 4), o_scr = add(h->srv_cur_replicas, Sz, Sc, 4), o_scc = add(h->srv_cur_cost, Sz, Sc, 4);
     const size_t total = off;
+    ctx->Scap = Scap; ctx->Mcap = Mcap; ctx->off_cap = o_cap;
+    {
+        const size_t os_[15] = {o_sm, o_sar, o_sin, o_sout, o_stt, o_sit, o_stp, o_stv, o_spr, o_smr, o_smb, o_ska, o_sca, o_scr, o_scc};
+        const size_t op_[8] = {o_pa, o_pb, o_pg, o_pd, o_pmb, o_pat, o_pac, o_pv};
+        for (int i = 0; i < 15; ++i) ctx->off_srv[i] = os_[i];
+        for (int i = 0; i < 8; ++i) ctx->off_perf[i] = op_[i];
+    }
+    ctx->last_h2d_bytes = (int64_t)total;
     CK(ctx->arena.ensure(total));
     CK(ctx->staging.ensure(total));
     char* st = (char*)ctx->staging.p;
@@ -456,27 +498,12 @@ int wva_system_upload(wva_ctx* ctx, const wva_system_soa* h) {
     ds.srv_cur_acc = (const int*)(d + o_sca); ds.srv_cur_replicas = (const int*)(d + o_scr); ds.srv_cur_cost = (const float*)(d + o_scc);
     ctx->S = S; ctx->A = A; ctx->M = M; ctx->T = T;
     ctx->s0 = 0; ctx->ns = S;
-    // N of CreateAllocation (allocation.go:77-87) per pair, or an upper bound where the device finds the
-    // pair unusable (it then needs no table at all): sizes the tables of the warp-per-pair kernel without
-    // a device round trip
+    // host copies of what sizes the pair tables
+    ctx->h_srv_model.assign(h->srv_model, h->srv_model + S); ctx->h_srv_out.assign(h->srv_out_tokens, h->srv_out_tokens + S);
+    ctx->h_srv_mb.assign(h->srv_max_batch, h->srv_max_batch + S); ctx->h_srv_arr.assign(h->srv_arrival_rpm, h->srv_arrival_rpm + S);
+    ctx->h_pmb.assign(h->perf_max_batch, h->perf_max_batch + MA); ctx->h_pat.assign(h->perf_at_tokens, h->perf_at_tokens + MA);
     ctx->hostN.assign((size_t)S * A, 0);
-    for (int s = 0; s < S; ++s) {
-        const int m = h->srv_model[s];
-        const long long outTok = h->srv_out_tokens[s];
-        if (h->srv_arrival_rpm[s] == 0.0f || outTok == 0) continue;
-        for (int a = 0; a < A; ++a) {
-            long long n;
-            if (h->srv_max_batch[s] > 0) n = h->srv_max_batch[s];
-            else if (m < 0) n = 0;
-            else {
-                const size_t pi = (size_t)m * A + a;
-                const long long prod = (long long)((unsigned long long)(long long)h->perf_max_batch[pi] * (unsigned long long)(long long)h->perf_at_tokens[pi]);
-                n = (outTok == -1) ? (long long)(0ull - (unsigned long long)prod) : prod / outTok;
-                if (n < 1) n = 1;
-            }
-            ctx->hostN[(size_t)s * A + a] = n;
-        }
-    }
+    host_plan_rows(ctx, 0, S);
     ctx->plan_valid = false;
     ctx->have_system = true;
     ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
@@ -1654,6 +1681,154 @@ int wva_solve_arrays(wva_ctx* ctx, int32_t unlimited, int32_t delayed_best_effor
     spec.unlimited = unlimited; spec.delayed_best_effort = delayed_best_effort; spec.saturation_policy = saturation_policy;
     wva_alloc_soa o = make_alloc_soa(acc, num_replicas, batch_size, cost, value, itl, ttft, rho, max_arrv_rate_per_replica);
     return wva_solve(ctx, &spec, chosen_acc, &o);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// incremental updates of the resident image (pkg/core/system.go:99-171)
+// ---------------------------------------------------------------------------------------------
+namespace {
+void invalidate_after_update(wva_ctx* ctx) {
+    ctx->s0 = 0; ctx->ns = ctx->S;
+    ctx->dsys.S = ctx->S; ctx->dsys.M = ctx->M;
+    ctx->plan_valid = false;
+    ctx->pairs_valid = ctx->pairs_complete = ctx->solved = ctx->grid_valid = false;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t wva_upload_bytes(const wva_ctx* ctx) { return ctx ? ctx->last_h2d_bytes : 0; }
+
+int wva_system_dims(const wva_ctx* ctx, int32_t* n_servers, int32_t* n_accels, int32_t* n_models, int32_t* n_types) {
+    if (!ctx) return WVA_EINVAL;
+    if (n_servers) *n_servers = ctx->S;
+    if (n_accels) *n_accels = ctx->A;
+    if (n_models) *n_models = ctx->M;
+    if (n_types) *n_types = ctx->T;
+    return WVA_OK;
+}
+
+int wva_system_update_servers(wva_ctx* ctx, int32_t first, int32_t count, const wva_system_soa* r) {
+    if (!ctx || !r || count < 0 || first < 0) return fail(ctx, WVA_EINVAL, "bad argument");
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    if (r->n_servers != count) return fail(ctx, WVA_EINVAL, "rows->n_servers must equal count");
+    if (first > ctx->S) return fail(ctx, WVA_EINVAL, "rows must be contiguous with the image (first <= S)");
+    if ((long long)first + count > ctx->Scap) return fail(ctx, WVA_ECAPACITY, "no spare server rows left: upload the image again");
+    if (((size_t)first + (size_t)count) * (size_t)ctx->A > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "S*A exceeds 2^31-1");
+    for (int i = 0; i < count; ++i) {
+        if (r->srv_model[i] >= ctx->M) return fail(ctx, WVA_EINVAL, "srv_model out of range");
+        if (r->srv_cur_acc[i] < WVA_ACC_UNKNOWN || r->srv_cur_acc[i] >= ctx->A) return fail(ctx, WVA_EINVAL, "srv_cur_acc out of range");
+        if (r->srv_priority[i] < 1 || r->srv_priority[i] > 100) return fail(ctx, WVA_EINVAL, "srv_priority must be in [1,100]");
+    }
+    if (count == 0) { ctx->last_h2d_bytes = 0; return WVA_OK; }
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, WVA_PHASE_UPLOAD);
+    const void* src[15] = {r->srv_model, r->srv_arrival_rpm, r->srv_in_tokens, r->srv_out_tokens, r->srv_slo_ttft, r->srv_slo_itl, r->srv_slo_tps,
+                           r->srv_target_valid, r->srv_priority, r->srv_min_replicas, r->srv_max_batch, r->srv_keep_acc, r->srv_cur_acc,
+                           r->srv_cur_replicas, r->srv_cur_cost};
+    const size_t elem[15] = {4, 4, 4, 4, 4, 4, 4, 1, 4, 4, 4, 1, 4, 4, 4};
+    // one pinned staging block, one async copy per array (the touched rows only)
+    size_t need = 0;
+    for (int k = 0; k < 15; ++k) need += align_up((size_t)count * elem[k], 16);
+    CK(cudaStreamSynchronize(ctx->stream));                      // the staging buffer may still feed an earlier copy
+    CK(ctx->staging.ensure(need));
+    char* st = (char*)ctx->staging.p;
+    char* d = ctx->arena.as<char>();
+    size_t so = 0; int64_t moved = 0;
+    for (int k = 0; k < 15; ++k) {
+        const size_t bytes = (size_t)count * elem[k];
+        std::memcpy(st + so, src[k], bytes);
+        CK(cudaMemcpyAsync(d + ctx->off_srv[k] + (size_t)first * elem[k], st + so, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        so += align_up(bytes, 16); moved += (int64_t)bytes;
+    }
+    const int newS = first + count > ctx->S ? first + count : ctx->S;
+    ctx->h_srv_model.resize((size_t)newS); ctx->h_srv_out.resize((size_t)newS); ctx->h_srv_mb.resize((size_t)newS); ctx->h_srv_arr.resize((size_t)newS);
+    for (int i = 0; i < count; ++i) {
+        ctx->h_srv_model[(size_t)first + i] = r->srv_model[i]; ctx->h_srv_out[(size_t)first + i] = r->srv_out_tokens[i];
+        ctx->h_srv_mb[(size_t)first + i] = r->srv_max_batch[i]; ctx->h_srv_arr[(size_t)first + i] = r->srv_arrival_rpm[i];
+    }
+    ctx->S = newS;
+    ctx->hostN.resize((size_t)newS * ctx->A, 0);
+    host_plan_rows(ctx, first, first + count);
+    ctx->last_h2d_bytes = moved;
+    invalidate_after_update(ctx);
+    timer.stop();
+    return WVA_OK;
+}
+
+int wva_system_update_models(wva_ctx* ctx, int32_t first, int32_t count, const wva_system_soa* r) {
+    if (!ctx || !r || count < 0 || first < 0) return fail(ctx, WVA_EINVAL, "bad argument");
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    if (r->n_models != count) return fail(ctx, WVA_EINVAL, "rows->n_models must equal count");
+    if (first > ctx->M) return fail(ctx, WVA_EINVAL, "rows must be contiguous with the image (first <= M)");
+    if ((long long)first + count > ctx->Mcap) return fail(ctx, WVA_ECAPACITY, "no spare model rows left: upload the image again");
+    if (count == 0) { ctx->last_h2d_bytes = 0; return WVA_OK; }
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, WVA_PHASE_UPLOAD);
+    const int A = ctx->A;
+    const void* src[8] = {r->perf_alpha, r->perf_beta, r->perf_gamma, r->perf_delta, r->perf_max_batch, r->perf_at_tokens, r->perf_acc_count, r->perf_valid};
+    const size_t elem[8] = {4, 4, 4, 4, 4, 4, 4, 1};
+    const size_t n = (size_t)count * A;
+    size_t need = 0;
+    for (int k = 0; k < 8; ++k) need += align_up(n * elem[k], 16);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->staging.ensure(need));
+    char* st = (char*)ctx->staging.p;
+    char* d = ctx->arena.as<char>();
+    size_t so = 0; int64_t moved = 0;
+    for (int k = 0; k < 8; ++k) {
+        const size_t bytes = n * elem[k];
+        std::memcpy(st + so, src[k], bytes);
+        CK(cudaMemcpyAsync(d + ctx->off_perf[k] + (size_t)first * A * elem[k], st + so, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        so += align_up(bytes, 16); moved += (int64_t)bytes;
+    }
+    const int newM = first + count > ctx->M ? first + count : ctx->M;
+    ctx->h_pmb.resize((size_t)newM * A, 0); ctx->h_pat.resize((size_t)newM * A, 0);
+    for (size_t i = 0; i < n; ++i) { ctx->h_pmb[(size_t)first * A + i] = r->perf_max_batch[i]; ctx->h_pat[(size_t)first * A + i] = r->perf_at_tokens[i]; }
+    ctx->M = newM;
+    // servers of the touched models get a new table plan
+    for (int s = 0; s < ctx->S; ++s) { const int m = ctx->h_srv_model[(size_t)s]; if (m >= first && m < first + count) host_plan_rows(ctx, s, s + 1); }
+    ctx->last_h2d_bytes = moved;
+    invalidate_after_update(ctx);
+    timer.stop();
+    return WVA_OK;
+}
+
+int wva_system_remove_server(wva_ctx* ctx, int32_t index) {
+    if (!ctx) return WVA_EINVAL;
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    if (index < 0 || index >= ctx->S) return fail(ctx, WVA_EINVAL, "server index out of range");
+    CK(cudaSetDevice(ctx->device));
+    const int last = ctx->S - 1, A = ctx->A;
+    if (index != last) {
+        k_server_move<<<1, 32, 0, ctx->stream>>>(ctx->dsys, last, index);
+        LAUNCH_CHECK();
+        ctx->h_srv_model[(size_t)index] = ctx->h_srv_model[(size_t)last]; ctx->h_srv_out[(size_t)index] = ctx->h_srv_out[(size_t)last];
+        ctx->h_srv_mb[(size_t)index] = ctx->h_srv_mb[(size_t)last]; ctx->h_srv_arr[(size_t)index] = ctx->h_srv_arr[(size_t)last];
+        for (int a = 0; a < A; ++a) ctx->hostN[(size_t)index * A + a] = ctx->hostN[(size_t)last * A + a];
+    }
+    ctx->S = last;
+    ctx->h_srv_model.resize((size_t)last); ctx->h_srv_out.resize((size_t)last); ctx->h_srv_mb.resize((size_t)last); ctx->h_srv_arr.resize((size_t)last);
+    ctx->hostN.resize((size_t)last * A);
+    ctx->last_h2d_bytes = 0;
+    invalidate_after_update(ctx);
+    return WVA_OK;
+}
+
+int wva_system_set_capacity(wva_ctx* ctx, const int64_t* type_capacity) {
+    if (!ctx || !type_capacity) return fail(ctx, WVA_EINVAL, "null argument");
+    if (!ctx->have_system) return fail(ctx, WVA_ESTATE, "no system uploaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t bytes = (size_t)ctx->T * 8;
+    CK(ctx->staging.ensure(bytes));
+    std::memcpy(ctx->staging.p, type_capacity, bytes);
+    CK(cudaMemcpyAsync(ctx->arena.as<char>() + ctx->off_cap, ctx->staging.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_h2d_bytes = (int64_t)bytes;
+    ctx->solved = false;                                     // the candidates (pairs) do not depend on capacities
+    return WVA_OK;
 }
 
 }  // extern "C"

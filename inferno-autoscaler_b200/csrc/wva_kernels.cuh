@@ -1878,6 +1878,16 @@ __global__ void k_totals_merge(int T, int n_ranks, const unsigned char* __restri
     count[t] = c; cost[t] = k;
 }
 
+// RemoveServer (system.go:165-171) on the resident image: the last server's row moves into the freed slot.
+__global__ void k_server_move(DevSystem sys, int from, int to) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+#define MV(field, T) const_cast<T*>(sys.field)[to] = sys.field[from];
+    MV(srv_model, int) MV(srv_arrival_rpm, float) MV(srv_in_tokens, int) MV(srv_out_tokens, int) MV(srv_slo_ttft, float)
+    MV(srv_slo_itl, float) MV(srv_slo_tps, float) MV(srv_target_valid, unsigned char) MV(srv_priority, int) MV(srv_min_replicas, int)
+    MV(srv_max_batch, int) MV(srv_keep_acc, unsigned char) MV(srv_cur_acc, int) MV(srv_cur_replicas, int) MV(srv_cur_cost, float)
+#undef MV
+}
+
 // ---- multi-rank exchange of the candidate records (limited mode) -----------------------------
 // One chunk per rank: {int first_pair, n_pairs, pad, pad} then SoA sections of `cap` records each
 // (replicas i64, batch i64, accelerator i32, 6 x f32, feasible u8 = 45 B per record).
