@@ -280,8 +280,9 @@ int wva_pairs_commit(wva_ctx* ctx);
  * would run a long constant-rate tail are first evaluated from the ramp plus the geometric closed form and
  * accepted only when every float32 rounding of the result is unambiguous within a proven error bound;
  * otherwise the exact chain runs.  Results are identical in every mode.
- *   on = 1 (default): one WARP per (server, accelerator, replicas) row, lanes = 32 consecutive batch sizes,
- *           the row's ramp built by warp scans (k_grid_scan);  on = 33: same, register allocation for 3 blocks/SM;
+ *   on = 1 (default): one WARP per (server, accelerator, replicas) row, lanes = 32 consecutive batch sizes:
+ *           k_scan_prep finds every row's exact stop, k_scan_cert evaluates the batch sizes before it (ramp
+ *           by warp scans + certificate), k_scan_lean the ones after it (frozen exact sums);
  *   on = 0: no certificate, exact chains only (one thread per candidate);
  *   on = 17: round-1 automatic choice: one thread per row (shared sequential ramp) for shards with >= 32 K rows,
  *           one thread per candidate below;  on = 3 / 5 / 9: always one thread per candidate / one thread per

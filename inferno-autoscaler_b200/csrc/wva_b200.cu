@@ -180,7 +180,7 @@ struct wva_ctx {
     int pairs_smem = 1;
     int certified = 1;
     int grid_rows = 1;
-    int grid_scan = 1;          // certified sweeps: 1 = warp-per-row scan kernel (default), 0 = the round-1 kernels; 2 = scan with 3 blocks/SM
+    int grid_scan = 1;          // certified sweeps: 1 = the scan kernels k_scan_prep / k_scan_cert / k_scan_lean (default), 0 = the round-1 kernels
     int pairs_debug = 0;
     DevBuf pairDbg;
 
@@ -197,7 +197,7 @@ struct wva_ctx {
 
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
-    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch;
+    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch, rowInfo;
     int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0, last_heavy_slice = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     // solve / totals phases: own event pairs, read lazily (a call that returns nothing to the host does not
@@ -354,7 +354,7 @@ int wva_ctx_create(int device, wva_ctx** out) {
     {
         const void* kernels[] = {(const void*)k_grid, (const void*)k_grid_rows, (const void*)k_grid_wrow, (const void*)k_grid_list,
                                  (const void*)k_grid_list_warp, (const void*)k_pairs_warp, (const void*)k_pairs, (const void*)k_grid_claim,
-                                 (const void*)k_grid_best_init, (const void*)k_grid_scan<2>, (const void*)k_grid_scan<3>};
+                                 (const void*)k_grid_best_init, (const void*)k_scan_prep, (const void*)k_scan_cert, (const void*)k_scan_lean};
         if (!std::getenv("WVA_NO_CARVEOUT"))
             for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaGetLastError();
@@ -374,7 +374,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
                       &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->pairPbuf, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
-                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->ioA, &ctx->ioB,
+                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->rowInfo, &ctx->ioA, &ctx->ioB,
                       &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG, &ctx->commTotals, &ctx->commChunk, &ctx->commGather};
     for (DevBuf* b : bufs) b->release();
     ctx->staging.release();
@@ -683,7 +683,7 @@ int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
     ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : ((on & 8) ? 3 : 1));
     // bits 1-3 select one of the round-1 kernels explicitly (and switch the scan kernel off); bit 4 (16): round-1
     // automatic choice (k_grid / k_grid_rows by shard size); bit 5 (32): scan kernel tuned for 3 blocks per SM
-    ctx->grid_scan = ((on & (2 | 4 | 8 | 16)) || !(on & 1)) ? 0 : ((on & 32) ? 2 : 1);
+    ctx->grid_scan = ((on & (2 | 4 | 8 | 16)) || !(on & 1)) ? 0 : 1;
     ctx->dsys.cert = ctx->certified;
     return WVA_OK;
 }
@@ -847,8 +847,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     if (smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_grid_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_grid_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_scan_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_scan_cert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // k_grid_wrow: the table, then per warp the checkpoints and the quotient buffer of warp_exact
     const size_t smemW = align_up(smem, 16) + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8;
@@ -856,8 +856,10 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
     if (slicePairsMax * (size_t)gp.n_rchunks > 0x7fffffffULL) return fail(ctx, WVA_EINVAL, "too many grid blocks");
     {
         const size_t perPairBlocks = (size_t)(gp.n_rchunks > gp.n_bseg ? gp.n_rchunks : gp.n_bseg);
-        CK(ctx->blockSlot.ensure((slicePairsMax * perPairBlocks + 1) * sizeof(GridSlot)));
+        CK(ctx->blockSlot.ensure((slicePairsMax * perPairBlocks * (scanMode ? 2 : 1) + 1) * sizeof(GridSlot)));
+        if (scanMode) CK(ctx->rowInfo.ensure((slicePairsMax * (size_t)r_max + 1) * sizeof(ScanRow)));
     }
+    gp.row_info = scanMode ? ctx->rowInfo.as<ScanRow>() : nullptr;
     gp.block_slot = ctx->blockSlot.as<GridSlot>();
     const long long stride = 11LL * b_max + 1;
 
@@ -886,8 +888,14 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
             CK(cudaEventRecord(ctx->evk0, ctx->gstream));
-            if (scanMode && ctx->grid_scan == 2) k_grid_scan<3><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
-            else if (scanMode) k_grid_scan<2><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+            if (scanMode) {
+                // exact stop of every row, then the two halves of the sweep (before / after the stop)
+                k_scan_prep<<<(unsigned)nBlocks, WVA_SCAN_MAXROWS, smem, ctx->gstream>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
+                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
+                k_scan_lean<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, 0, ctx->gstream>>>(ctx->dsys, gp);
+            }
             else if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);
             else k_grid<<<(unsigned)nBlocks, WVA_GRID_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
@@ -966,7 +974,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         }
         // winners of the slice: the slot that carries a server's minimum key writes its record
         if (nBlocks > 0) {
-            k_grid_claim<<<(unsigned)((nBlocks + 255) / 256), 256, 0, ctx->gstream>>>(gp, gp.block_slot, (int)nBlocks, ctx->bestDev.as<wva_grid_best>());
+            const size_t nSlots = scanMode ? 2 * nBlocks : nBlocks;       // k_scan_cert and k_scan_lean each publish one slot per block
+            k_grid_claim<<<(unsigned)((nSlots + 255) / 256), 256, 0, ctx->gstream>>>(gp, gp.block_slot, (int)nSlots, ctx->bestDev.as<wva_grid_best>());
             LAUNCH_CHECK();
         }
         if (listSlots > 0) {

@@ -44,7 +44,7 @@ __device__ __forceinline__ double rcp_pos(double x) { return rcp_refined(x); }
 // The certificate of cert_eval with the divisions folded into two reciprocals.  yTail = rcp_refined(sTail).
 // Own error (relative, units of u): oneR, r <= 2; inv <= 4; T0 <= 7, T1 <= 11 (+ the exp/log1p term of cert_eval when
 // x < 140: <= 80 on 1 - r^M (1 + x)); S, U <= 100; invS <= 102; every aggregate <= 128.
-__device__ __forceinline__ bool cert_eval_fast(const double pN, const double sumRamp, const double uN, const double lam,
+__device__ __noinline__ bool cert_eval_fast(const double pN, const double sumRamp, const double uN, const double lam,
                                                const double sTail, const double yTail, const int N, const int K,
                                                const float lambda, SolveStats& o) {
     const int M = K - N;
@@ -96,13 +96,13 @@ __device__ __forceinline__ double shfl_up_d(double v, int o) { return __shfl_up_
 // sequential arithmetic (the "stopped" path of k_grid_rows, same rule, same code shape):
 //   stopB   first batch size whose candidates use the frozen exact sums (INT_MAX: the row never stops)
 //   brokenB first batch size from which the row must go to the exact-chain kernels (window exit in the exact ramp)
-struct ScanRow { int stopB, brokenB; double exInSys, exSumP; };
+struct ScanRow { int stopB, brokenB; double exInSys, exSumP; int nGood, pad; };   // nGood: table entries [0, nGood) are usable (pair-wide)
 
 // The exact ramp of one row up to its stop: the reference's recurrence, sequential, bit-identical
 // (mm1modelstatedependent.go:77-112), with solve_stream's truncation rule at a 2^10 stricter threshold.
-__device__ __forceinline__ void scan_row_exact(const double* rateD, const double* rcp, const float* rateF, const int B, const int nGood,
+__device__ __noinline__ void scan_row_exact(const double* rateD, const double* rcp, const float* rateF, const int B, const int nGood,
                                                const bool tame, const float lambda, ScanRow& out, unsigned long long& steps) {
-    out.stopB = 0x7fffffff; out.brokenB = 0x7fffffff; out.exInSys = 0.0; out.exSumP = 0.0;
+    out.stopB = 0x7fffffff; out.brokenB = 0x7fffffff; out.exInSys = 0.0; out.exSumP = 0.0; out.nGood = nGood; out.pad = 0;
     const double lam = (double)lambda;
     if (!(lam >= 0x1p-100 && lam <= 0x1p20)) { out.brokenB = 1; return; }
     // a row stops only after its ratios have dropped under 0.998: with a tame (non-decreasing) table that never
@@ -139,113 +139,314 @@ __device__ __forceinline__ void scan_row_exact(const double* rateD, const double
     }
 }
 
-// MINB = resident blocks per SM the register allocation is tuned for -- both instantiated, chosen at run time
-// (wva_set_certified_tails).
+// the sweep's last resort when the deferred list is full: the exact chain right here (out of line: it is never
+// on the common path and must not cost the main loop registers)
+__device__ __noinline__ int scan_exact_inline(const float* rateF, const double* rateD, const double* rcp, const GridServer& gs, int b, float rate,
+                                              bool tame, wva_metrics& m, unsigned long long& steps) {
+    ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
+    float rt, dc;
+    return analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The sweep as three kernels, so that each gets the register allocation (and occupancy) its work needs:
+//
+//   k_scan_prep   block = (pair, chunk of rows), one THREAD per row: builds the pair's {rate, reciprocal} table
+//                 (published in gp.pair_tab for the other kernels), runs the exact ramp of every row to its stop
+//                 (scan_row_exact) and leaves one ScanRow per row in gp.row_info; fills the status / cube of pairs
+//                 whose lookups fail.
+//   k_scan_cert   one WARP per row, the batch sizes BEFORE the row's stop: ramp by warp scans + cert_eval_fast
+//                 (FP64-heavy, ~100 registers).
+//   k_scan_lean   one WARP per row, the batch sizes FROM the row's stop on: the reference's sums are frozen there,
+//                 a candidate is a dozen float32 operations and a 33-byte store (few registers, high occupancy;
+//                 bound by the cube's HBM write).  In the synthetic sets ~13 of a row's 16 chunks are of this kind.
+// k_scan_cert and k_scan_lean write disjoint candidates; a 32-candidate chunk that contains the stop belongs to
+// k_scan_cert entirely.
+// ---------------------------------------------------------------------------------------------------------------
 #define WVA_SCAN_WARPS 8
 #define WVA_SCAN_MAXROWS 64        /* rows (replica counts) per block */
-template <int MINB>
-__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, MINB)
-k_grid_scan(DevSystem sys, GridParams gp) {
+
+struct ScanBlock {                 // what every kernel derives from blockIdx
+    int pairSlice, rBeg, rEnd, pairLocal, sl, a, s;
+};
+__device__ __forceinline__ ScanBlock scan_block(const DevSystem& sys, const GridParams& gp) {
+    ScanBlock k;
+    k.pairSlice = blockIdx.x / gp.n_rchunks;
+    const int rchunk = blockIdx.x % gp.n_rchunks;
+    k.rBeg = rchunk * gp.r_chunk + 1;
+    k.rEnd = (k.rBeg + gp.r_chunk - 1 < gp.r_max) ? k.rBeg + gp.r_chunk - 1 : gp.r_max;
+    k.pairLocal = gp.pair_base + k.pairSlice;
+    k.sl = k.pairLocal / sys.A; k.a = k.pairLocal % sys.A;
+    k.s = gp.s0 + k.sl;
+    return k;
+}
+// pair usable for the sweep?  (status of all its candidates otherwise)
+__device__ __forceinline__ int scan_pair_status(const DevSystem& sys, int s, int a, GridServer& gs) {
+    if (!(pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a))) return WVA_CAND_ERR_PAIR;
+    load_grid_server(sys, s, a, gs);
+    if (gs.inTok < 0 || gs.outTok < 1 || gs.sloTTFT < 0.0f || gs.sloITL < 0.0f || gs.sloTPS < 0.0f) return WVA_CAND_ERR_CONFIG;
+    return WVA_CAND_OK;
+}
+
+__global__ void __launch_bounds__(WVA_SCAN_MAXROWS)
+k_scan_prep(DevSystem sys, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* rateD = reinterpret_cast<double*>(smem_raw);
     double* rcp = rateD + gp.b_max;
     float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
     __shared__ int sh_nGood;
-    __shared__ unsigned long long sh_key;
-    __shared__ unsigned long long sh_cnt[3];
-    __shared__ ScanRow sh_row[WVA_SCAN_MAXROWS];
-
-    // block = (pair, chunk of replica counts): small shards split a pair's rows over n_rchunks blocks
-    const int pairSlice = blockIdx.x / gp.n_rchunks, rchunk = blockIdx.x % gp.n_rchunks;
-    const int rBeg = rchunk * gp.r_chunk + 1;
-    const int rEnd = (rBeg + gp.r_chunk - 1 < gp.r_max) ? rBeg + gp.r_chunk - 1 : gp.r_max;
-    const int pairLocal = gp.pair_base + pairSlice;
-    const int sl = pairLocal / sys.A, a = pairLocal % sys.A;
-    const int s = gp.s0 + sl;
+    const ScanBlock k = scan_block(sys, gp);
     const int B = gp.b_max, R = gp.r_max;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0) {
-        sh_nGood = B; sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0;
-        gp.block_slot[blockIdx.x].key = WVA_KEY_NONE;
-    }
-    const bool pairOk = pair_lookups_ok(sys, s, a) && is_candidate_accel(sys, s, a);
+    if (threadIdx.x == 0) sh_nGood = B;
     GridServer gs;
-    int blockStatus = WVA_CAND_OK;
-    if (!pairOk) blockStatus = WVA_CAND_ERR_PAIR;
-    else {
-        load_grid_server(sys, s, a, gs);
-        if (gs.inTok < 0 || gs.outTok < 1 || gs.sloTTFT < 0.0f || gs.sloITL < 0.0f || gs.sloTPS < 0.0f)
-            blockStatus = WVA_CAND_ERR_CONFIG;
-    }
-    const size_t candBase = ((size_t)pairLocal * R) * (size_t)B;
+    const int blockStatus = scan_pair_status(sys, k.s, k.a, gs);
+    const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
+    ScanRow* rowInfo = gp.row_info + (size_t)k.pairSlice * R;
     if (blockStatus != WVA_CAND_OK) {
-        const size_t n = (size_t)(rEnd - rBeg + 1) * B, off = (size_t)(rBeg - 1) * B;
+        const size_t n = (size_t)(k.rEnd - k.rBeg + 1) * B, off = (size_t)(k.rBeg - 1) * B;
         if (gp.cube) {
             float4* c = reinterpret_cast<float4*>(&gp.cube[candBase + off]);
             const float4 z = make_float4(0, 0, 0, 0);
             for (size_t j = threadIdx.x; j < 2 * n; j += blockDim.x) c[j] = z;
         }
         if (gp.status) for (size_t j = threadIdx.x; j < n; j += blockDim.x) gp.status[candBase + off + j] = (unsigned char)blockStatus;
+        for (int rr = threadIdx.x; rr <= k.rEnd - k.rBeg; rr += blockDim.x) { ScanRow row; row.stopB = row.brokenB = -1; row.exInSys = row.exSumP = 0.0; row.nGood = 0; row.pad = 0; rowInfo[k.rBeg - 1 + rr] = row; }
         return;
     }
     __syncthreads();
     ServFormula sf; sf.init(gs.sp, gs.inTok, gs.outTok);
-    double2* gtab = gp.pair_tab + (size_t)pairSlice * B;
+    double2* gtab = gp.pair_tab + (size_t)k.pairSlice * B;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         const float rt = sf.rate(i + 1);
         rateF[i] = rt;
         const double d = (double)rt;
         const double y = rcp_refined(d);
         rateD[i] = d; rcp[i] = y;
-        if (rchunk == 0) gtab[i] = make_double2(d, y);          // the exact-chain kernels read the table back
+        if (k.rBeg == 1) gtab[i] = make_double2(d, y);          // one block per pair publishes the table
         if (!(rt > 0.0f) || !(rt < CUDART_INF_F)) atomicMin(&sh_nGood, i);
     }
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
     __syncthreads();
     const int nGood = sh_nGood;
-
-    unsigned long long steps = 0, algSteps = 0, okCount = 0;
-    // ---- phase A: one thread per row runs the exact ramp to the row's stop --------------------------------------
-    for (int rr = threadIdx.x; rr <= rEnd - rBeg; rr += blockDim.x) {
-        const float lambdaA = (gs.totalRate / (float)(rBeg + rr)) / 1000.0f;
+    unsigned long long steps = 0;
+    for (int rr = threadIdx.x; rr <= k.rEnd - k.rBeg; rr += blockDim.x) {
+        const float lambdaA = (gs.totalRate / (float)(k.rBeg + rr)) / 1000.0f;
         ScanRow row;
         scan_row_exact(rateD, rcp, rateF, B, nGood, tame, lambdaA, row, steps);
-        sh_row[rr] = row;
+        rowInfo[k.rBeg - 1 + rr] = row;
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&gp.counters[0], steps);
+}
+
+// metrics, feasibility and key of one analysed candidate from its float32 statistics; stores cube + status
+struct ScanRowCtx {                // row constants
+    float rate, lambda; unsigned long long rowKey; bool valueOk, repOk;
+    wva_metrics* rowCube; unsigned char* rowStatus;
+};
+__device__ __forceinline__ void scan_finish(const GridServer& gs, const ScanRowCtx& rc, const SolveStats& so, const int n, const float rateMax,
+                                            unsigned long long& bestKey, float& bestItl, float& bestTtft, float& bestRho) {
+    const int b = n + 1;
+    const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
+    float rho = so.avgNumInServers / (float)b;
+    if (!(rho > 0.0f && rho <= 1.0f)) rho = go_minf(go_maxf(rho, 0.0f), 1.0f);      // the clamp only matters outside (0, 1]
+    const float prefill = prefill_time(gs.sp, gs.inTok, effConc);
+    const float token = decode_time(gs.sp, effConc);
+    const float lamMaxBack = rateMax / 1000.0f;
+    const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+    const float ttft = so.avgWaitTime + prefill;
+    const bool feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || token <= gs.sloITL) &&
+                          (!(gs.sloTPS > 0.0f) || rc.rate <= rateTPS) && rc.repOk;
+    if (feasible && rc.valueOk) {
+        const unsigned long long key = rc.rowKey + (unsigned long long)n;
+        if (key < bestKey) { bestKey = key; bestItl = token; bestTtft = ttft; bestRho = rho; }
+    }
+    if (rc.rowCube) {
+        float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
+        c[0] = make_float4(so.throughput * 1000.0f, so.avgRespTime, so.avgWaitTime, so.avgNumInServers);
+        c[1] = make_float4(prefill, token, rateMax, rho);
+    }
+    if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
+}
+__device__ __forceinline__ void scan_store_error(const ScanRowCtx& rc, const int n, const int st) {
+    if (rc.rowCube) {
+        float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
+        const float4 z = make_float4(0, 0, 0, 0);
+        c[0] = z; c[1] = z;
+    }
+    if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)st;
+}
+__device__ __forceinline__ ScanRowCtx scan_row_ctx(const GridServer& gs, const GridParams& gp, const int a, const int r, const size_t candBase) {
+    ScanRowCtx rc;
+    rc.rate = gs.totalRate / (float)r;
+    rc.lambda = rc.rate / 1000.0f;
+    const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+    float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
+    value = value + 0.0f;
+    rc.valueOk = value == value;                               // a NaN value is never selected
+    rc.rowKey = make_key(value, a, r, 1);
+    rc.repOk = r >= gs.minReplicas;
+    const size_t rowBase = candBase + (size_t)(r - 1) * gp.b_max;
+    rc.rowCube = gp.cube ? gp.cube + rowBase : nullptr;
+    rc.rowStatus = gp.status ? gp.status + rowBase : nullptr;
+    return rc;
+}
+// block argmin + counters (shared by k_scan_cert / k_scan_lean); slotBase separates the two kernels' slots
+__device__ __forceinline__ void scan_block_reduce(const DevSystem& sys, const GridParams& gp, const GridServer& gs, const ScanBlock& k, const int slot,
+                                                  unsigned long long bestKey, float bestItl, float bestTtft, float bestRho,
+                                                  unsigned long long steps, unsigned long long algSteps, unsigned long long okCount,
+                                                  unsigned long long* sh_key, unsigned long long* sh_cnt) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long warpKey = bestKey;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
+        if (other < warpKey) warpKey = other;
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
+        okCount += __shfl_down_sync(0xffffffffu, okCount, o);
+    }
+    if (lane == 0) {
+        if (warpKey != WVA_KEY_NONE) atomicMin(sh_key, warpKey);
+        atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
     }
     __syncthreads();
+    const unsigned long long blockKey = *sh_key;
+    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {
+        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = k.sl; sl_.pad = 0;
+        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
+        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+        gp.block_slot[slot] = sl_;
+        atomicMin(&gp.keys[k.sl], blockKey);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
+    }
+}
 
-    // ---- phase B: one warp per row, lanes = 32 consecutive batch sizes ---------------------------------------------
-    unsigned long long bestKey = WVA_KEY_NONE;
+// ---- the batch sizes from a row's stop on: frozen exact sums ----------------------------------------------------------
+__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, 5)
+k_scan_lean(DevSystem sys, GridParams gp) {
+    __shared__ unsigned long long sh_key;
+    __shared__ unsigned long long sh_cnt[3];
+    const ScanBlock k = scan_block(sys, gp);
+    const int B = gp.b_max, R = gp.r_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = gridDim.x + blockIdx.x;                       // second half of gp.block_slot
+    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; }
+    GridServer gs;
+    if (scan_pair_status(sys, k.s, k.a, gs) != WVA_CAND_OK) return;       // k_scan_prep wrote the pair's status
+    __syncthreads();
+    const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
+    const double2* __restrict__ gtab = gp.pair_tab + (size_t)k.pairSlice * B;
+    const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
+    unsigned long long bestKey = WVA_KEY_NONE, algSteps = 0, okCount = 0;
     float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
-    for (int r = rBeg + warp; r <= rEnd; r += WVA_SCAN_WARPS) {
-        const float rate = gs.totalRate / (float)r;
-        const float lambda = rate / 1000.0f;
+    for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
+        const ScanRow row = rowInfo[r - 1];
+        if (row.stopB > B) continue;                                // the row never stops: all of it belongs to k_scan_cert
+        const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
+        const float lambda = rc.lambda;
+        const bool rateOk = rc.rate > 0.0f;
+        const double oneMinusSumP = 1.0 - row.exSumP;
+        const float inSysF = (float)row.exInSys;
+        const float tput = lambda * (1.0f - 0.0f);                  // throughput = lambda * (1 - float32(p[K])), p[K] rounds to 0
+        const float respRow = inSysF / tput;                        // avgRespTime: the same for every stopped candidate of the row
+        // first chunk that lies entirely at or after the stop (the chunk containing the stop is k_scan_cert's)
+        const int cFirst = ((row.stopB - 1 + 31) / 32) * 32;
+        for (int c0 = cFirst; c0 < B; c0 += 32) {
+            const int n = c0 + lane;
+            if (n >= B) continue;
+            if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides
+                const int k0 = atomicAdd(gp.slow_count, 1);
+                if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(candBase + (size_t)(r - 1) * B + n);
+                continue;
+            }
+            const float rateMax = ((float)gtab[n].x * (1.0f - WVA_EPSILON)) * 1000.0f;
+            if (!rateOk) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_LE0); continue; }
+            if (rc.rate > rateMax) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX); continue; }
+            if (lambda < 0.0f) { scan_store_error(rc, n, WVA_CAND_ERR_MODEL); continue; }
+            // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no longer change;
+            // float32(p[K]) < 2^-58 so throughput == lambda
+            SolveStats so;
+            const double inServ = row.exInSys + oneMinusSumP * (double)(n + 1);
+            so.avgNumInServers = (float)inServ;
+            so.avgNumInSystem = inSysF;
+            so.throughput = tput;
+            so.avgRespTime = respRow;
+            so.avgServTime = so.avgNumInServers / so.throughput;
+            so.avgWaitTime = so.avgRespTime - so.avgServTime;
+            if (so.avgWaitTime < 0.0f) so.avgWaitTime = 0.0f;
+            okCount++;
+            algSteps += 2ULL * (unsigned long long)(11 * (n + 1) + 1);
+            scan_finish(gs, rc, so, n, rateMax, bestKey, bestItl, bestTtft, bestRho);
+        }
+    }
+    scan_block_reduce(sys, gp, gs, k, slot, bestKey, bestItl, bestTtft, bestRho, 0ULL, algSteps, okCount, &sh_key, sh_cnt);
+}
+
+// ---- the batch sizes before a row's stop: ramp by warp scans + certificate --------------------------------------------
+__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, 2)
+k_scan_cert(DevSystem sys, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* rateD = reinterpret_cast<double*>(smem_raw);
+    double* rcp = rateD + gp.b_max;
+    float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
+    __shared__ unsigned long long sh_key;
+    __shared__ unsigned long long sh_cnt[3];
+    __shared__ int sh_need;
+    const ScanBlock k = scan_block(sys, gp);
+    const int B = gp.b_max, R = gp.r_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x;
+    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; sh_need = 0; }
+    GridServer gs;
+    if (scan_pair_status(sys, k.s, k.a, gs) != WVA_CAND_OK) return;
+    __syncthreads();
+    const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
+    const double2* __restrict__ gtab = gp.pair_tab + (size_t)k.pairSlice * B;
+    const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
+    // how far this block's rows reach before their stops (the table is only needed up to there)
+    int need = 0;
+    for (int rr = threadIdx.x; rr <= k.rEnd - k.rBeg; rr += blockDim.x) {
+        const ScanRow row = rowInfo[k.rBeg - 1 + rr];
+        const int lim = row.stopB > B ? B : ((row.stopB - 1 + 31) / 32) * 32;
+        need = need > lim ? need : lim;
+    }
+    if (need) atomicMax(&sh_need, need);
+    __syncthreads();
+    need = sh_need < B ? sh_need : B;
+    if (need == 0) return;                                          // every row of the block stops in its first chunk... and k_scan_lean has it
+    for (int i = threadIdx.x; i < need; i += blockDim.x) {
+        const double2 v = gtab[i];
+        rateD[i] = v.x; rcp[i] = v.y; rateF[i] = (float)v.x;
+    }
+    const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
+    __syncthreads();
+
+    unsigned long long bestKey = WVA_KEY_NONE, steps = 0, algSteps = 0, okCount = 0;
+    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
+        const ScanRow row = rowInfo[r - 1];
+        const int cEnd = row.stopB > B ? B : ((row.stopB - 1 + 31) / 32) * 32;       // chunks [0, cEnd) are this kernel's
+        if (cEnd == 0) continue;
+        const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
+        const float lambda = rc.lambda;
         const double lam = (double)lambda;
-        const float cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
-        float value = transition_penalty(gs.curAcc, gs.curRep, gs.curCost, a, (long long)r, cost);
-        value = value + 0.0f;
-        const bool valueOk = value == value;                       // a NaN value is never selected
-        const unsigned long long rowKey = make_key(value, a, r, 1);
-        const bool rateOk = rate > 0.0f;                            // else every candidate of the row is ERR_RATE_LE0
-        const bool repOk = r >= gs.minReplicas;
-        const ScanRow row = sh_row[r - rBeg];
-        wva_metrics* const rowCube = gp.cube ? gp.cube + candBase + (size_t)(r - 1) * B : nullptr;
-        unsigned char* const rowStatus = gp.status ? gp.status + candBase + (size_t)(r - 1) * B : nullptr;
+        const bool rateOk = rc.rate > 0.0f;
         const size_t rowBase = candBase + (size_t)(r - 1) * B;
+        const double oneMinusSumP = 1.0 - row.exSumP;
         // carries of the three scans: state 0 is p = 1, sum = 1, sum i p = 0
         double carryP = 1.0, carrySum = 1.0, carryU = 0.0;
         bool rowBroken = false;        // the scan ramp left the value window: later candidates need the exact chain
-        for (int c0 = 0; c0 < B; c0 += 32) {
+        for (int c0 = 0; c0 < cEnd; c0 += 32) {
             const int n = c0 + lane, b = n + 1;
             const bool inRow = n < B;
-            const bool tabOk = inRow && b <= nGood;
             const bool stoppedLane = b >= row.stopB;
             double p = 0.0, sum = 0.0, uN = 0.0;
-            bool broken = rowBroken || !tabOk || b >= row.brokenB;
-            if (c0 + 1 < row.stopB && c0 + 1 < row.brokenB && !rowBroken) {       // warp-uniform: some lane still needs the ramp
+            bool broken = rowBroken || !inRow || b >= row.brokenB || b > row.nGood;
+            if (c0 + 1 < row.brokenB && !rowBroken) {              // warp-uniform
                 // ---- ramp states c0+1 .. c0+32 by scans --------------------------------------------------------
-                double P = tabOk ? lam * rcp[n] : 1.0;
+                double P = (inRow && b <= row.nGood) ? lam * rcp[n] : 1.0;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(P, o); if (lane >= o) P *= t; }
                 p = carryP * P;
@@ -253,13 +454,13 @@ k_grid_scan(DevSystem sys, GridParams gp) {
                 bool laneBroken = false;
                 if (hq - WVA_WIN_LO >= WVA_WIN_SPAN) {
                     // below the window (0 and subnormals included) after the ratios have dropped under 0.998: died out
-                    const bool died = tabOk && (p >= 0.0) && (p < 0x1p-800) && tame && (lambda <= 0.998f * rateF[n]);
+                    const bool died = inRow && (p >= 0.0) && (p < 0x1p-800) && tame && (lambda <= 0.998f * rateF[n]);
                     if (died) p = 0.0; else laneBroken = inRow;
                 }
                 const unsigned brk = __ballot_sync(0xffffffffu, laneBroken);
                 const int firstBrk = brk ? (__ffs(brk) - 1) : 32;
                 broken = broken || lane >= firstBrk;
-                const double pUse = (lane < firstBrk && tabOk) ? p : 0.0;
+                const double pUse = (lane < firstBrk && inRow) ? p : 0.0;
                 double Ssum = pUse, Us = (double)b * pUse;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -276,115 +477,58 @@ k_grid_scan(DevSystem sys, GridParams gp) {
             }
             if (!inRow) continue;
             // ---- candidate (r, b) ----------------------------------------------------------------------
-            const int K = 11 * b;
-            const float lambdaMax = rateF[n] * (1.0f - WVA_EPSILON);
-            const float rateMax = lambdaMax * 1000.0f;
-            int st = WVA_CAND_OK;
-            bool feasible = false, skipWrite = false;
-            wva_metrics m;
-            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
-            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
-            if (b > nGood) {                                   // bad table entry: literal path decides
-                const int k = atomicAdd(gp.slow_count, 1);
-                if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)(rowBase + n);
-                skipWrite = true;
-            } else if (!rateOk) st = WVA_CAND_ERR_RATE_LE0;
-            else if (rate > rateMax) st = WVA_CAND_ERR_RATE_MAX;
-            else if (lambda < 0.0f) st = WVA_CAND_ERR_MODEL;
-            else {
-                SolveStats so;
-                bool certified = false;
-                if (!broken) {
-                    if (stoppedLane) {
-                        // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no
-                        // longer change; float32(p[K]) < 2^-58 so throughput == lambda
-                        const double inServ = row.exInSys + (1.0 - row.exSumP) * (double)b;
-                        finish_stats(so, lambda, inServ, row.exInSys, 0.0f);
-                        certified = true;
-                    } else certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
-                }
-                bool haveMetrics = false;
-                if (!certified) {
-                    // exact chain in the list kernels; when that list is full, right here
-                    const int k = atomicAdd(gp.heavy_count, 1);
-                    if (k < gp.heavy_cap) { gp.heavy_list[k] = (unsigned long long)(rowBase + n); gp.heavy_cost[k] = (float)K; skipWrite = true; }
-                    else {
-                        ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
-                        float rt, dc;
-                        const int st2 = analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
-                        if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); skipWrite = true; }
-                        else { st = st2; haveMetrics = true; }
-                    }
-                }
-                if (!skipWrite) {
-                    if (!haveMetrics) {
-                        // EffectiveConcurrency (queueanalyzer.go:296-302) with the row-invariant parts hoisted by the compiler
-                        const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
-                        float rho = so.avgNumInServers / (float)b;
-                        rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
-                        m.throughput = so.throughput * 1000.0f;
-                        m.avg_resp_time = so.avgRespTime;
-                        m.avg_wait_time = so.avgWaitTime;
-                        m.avg_num_in_serv = so.avgNumInServers;
-                        m.avg_prefill_time = prefill_time(gs.sp, gs.inTok, effConc);
-                        m.avg_token_time = decode_time(gs.sp, effConc);
-                        m.max_rate = rateMax;
-                        m.rho = rho;
-                    }
-                    if (st != WVA_CAND_OK) {
-                        m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
-                        m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
-                    } else {
-                        okCount++;
-                        algSteps += 2ULL * (unsigned long long)(K + 1);
-                        const float lamMaxBack = rateMax / 1000.0f;
-                        const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
-                        const float ttft = m.avg_wait_time + m.avg_prefill_time;
-                        const float itl = m.avg_token_time;
-                        feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
-                                   (!(gs.sloTPS > 0.0f) || rate <= rateTPS) && repOk;
-                        if (feasible && valueOk) {
-                            const unsigned long long key = rowKey + (unsigned long long)(b - 1);
-                            if (key < bestKey) { bestKey = key; bestItl = itl; bestTtft = ttft; bestRho = m.rho; }
-                        }
-                    }
-                }
+            const float rateMax = (rateF[n] * (1.0f - WVA_EPSILON)) * 1000.0f;
+            if (b > row.nGood) {                               // bad table entry: the literal path decides
+                const int k0 = atomicAdd(gp.slow_count, 1);
+                if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(rowBase + n);
+                continue;
             }
-            if (!skipWrite) {
-                if (rowCube) {
-                    float4* c = reinterpret_cast<float4*>(&rowCube[n]);
+            if (!rateOk) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_LE0); continue; }
+            if (rc.rate > rateMax) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX); continue; }
+            if (lambda < 0.0f) { scan_store_error(rc, n, WVA_CAND_ERR_MODEL); continue; }
+            const int K = 11 * b;
+            SolveStats so;
+            bool certified = false;
+            if (!broken) {
+                if (stoppedLane) {
+                    const double inServ = row.exInSys + oneMinusSumP * (double)b;
+                    finish_stats(so, lambda, inServ, row.exInSys, 0.0f);
+                    certified = true;
+                } else certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
+            }
+            if (!certified) {
+                // exact chain in the list kernels; when that list is full, right here.  (A bad table entry, b > nGood, was
+                // folded into brokenB by k_scan_prep: the list kernels hand those to the literal path.)
+                const int kk = atomicAdd(gp.heavy_count, 1);
+                if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)K; continue; }
+                wva_metrics m;
+                const int st2 = scan_exact_inline(rateF, rateD, rcp, gs, b, rc.rate, tame, m, steps);
+                if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); continue; }
+                if (st2 != WVA_CAND_OK) { scan_store_error(rc, n, st2); continue; }
+                // metrics are final: publish them the way scan_finish would
+                okCount++; algSteps += 2ULL * (unsigned long long)(K + 1);
+                const float rateTPS = ((rateMax / 1000.0f) * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+                const float ttft = m.avg_wait_time + m.avg_prefill_time;
+                const bool feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || m.avg_token_time <= gs.sloITL) &&
+                                      (!(gs.sloTPS > 0.0f) || rc.rate <= rateTPS) && rc.repOk;
+                if (feasible && rc.valueOk) {
+                    const unsigned long long key = rc.rowKey + (unsigned long long)n;
+                    if (key < bestKey) { bestKey = key; bestItl = m.avg_token_time; bestTtft = ttft; bestRho = m.rho; }
+                }
+                if (rc.rowCube) {
+                    float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
                     c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
                     c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
                 }
-                if (rowStatus) rowStatus[n] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+                if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
+                continue;
             }
+            okCount++;
+            algSteps += 2ULL * (unsigned long long)(K + 1);
+            scan_finish(gs, rc, so, n, rateMax, bestKey, bestItl, bestTtft, bestRho);
         }
     }
-    // ---- block argmin + counters ------------------------------------------------------------------
-    unsigned long long warpKey = bestKey;
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_down_sync(0xffffffffu, warpKey, o);
-        if (other < warpKey) warpKey = other;
-        steps += __shfl_down_sync(0xffffffffu, steps, o);
-        algSteps += __shfl_down_sync(0xffffffffu, algSteps, o);
-        okCount += __shfl_down_sync(0xffffffffu, okCount, o);
-    }
-    if (lane == 0) {
-        if (warpKey != WVA_KEY_NONE) atomicMin(&sh_key, warpKey);
-        atomicAdd(&sh_cnt[0], steps); atomicAdd(&sh_cnt[1], algSteps); atomicAdd(&sh_cnt[2], okCount);
-    }
-    __syncthreads();
-    const unsigned long long blockKey = sh_key;
-    if (blockKey != WVA_KEY_NONE && bestKey == blockKey) {
-        GridSlot sl_; sl_.key = blockKey; sl_.itl = bestItl; sl_.ttft = bestTtft; sl_.rho = bestRho; sl_.sl = sl; sl_.pad = 0;
-        const int r = (int)((blockKey >> 14) & 0x3ff) + 1;
-        sl_.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
-        gp.block_slot[blockIdx.x] = sl_;
-        atomicMin(&gp.keys[sl], blockKey);
-    }
-    if (threadIdx.x == 0) {
-        atomicAdd(&gp.counters[0], sh_cnt[0]); atomicAdd(&gp.counters[1], sh_cnt[1]); atomicAdd(&gp.counters[2], sh_cnt[2]);
-    }
+    scan_block_reduce(sys, gp, gs, k, slot, bestKey, bestItl, bestTtft, bestRho, steps, algSteps, okCount, &sh_key, sh_cnt);
 }
 
 }  // namespace wva

@@ -593,6 +593,7 @@ __global__ void k_pair_bucket_scatter(const long long* __restrict__ nIn, int nPa
 
 // best candidate of a block / a list thread: key + the metrics a wva_grid_best needs
 struct GridSlot { unsigned long long key; float cost, itl, ttft, rho; int sl; int pad; };
+struct ScanRow;
 
 struct GridParams {
     int r_max, b_max;
@@ -610,6 +611,7 @@ struct GridParams {
     struct GridSlot* list_slot;      // [heavy_cap + slow_cap] one per list-kernel thread
     int tail_cap;                    // tail steps a candidate may take inside k_grid before it is deferred
     unsigned long long* heavy_list; float* heavy_cost; int* heavy_count; int heavy_cap;   // deferred (long) chains
+    ScanRow* row_info;               // [slice pairs * r_max] k_scan_prep -> k_scan_cert / k_scan_lean
 };
 
 // order-preserving map float -> uint32 (ascending), -0 canonicalised by the caller
