@@ -65,20 +65,27 @@ def fp64_peak():
         return 148 * 64 * 1.965, "148 SMs x 64 lanes x 1.965 GHz"
 
 
-def ncu_summary(kernel, cfg_id):
-    """key metrics of `kernel` from the committed `ncu --set full` summary of the SAME workload (cube on),
-    profiles/ncu_full_<round>_cfg<k>.json; None when there is none."""
+def ncu_summary(kernels, cfg_id):
+    """dram traffic (read + write, summed over `kernels`) and the time-weighted FP64 pipe utilisation from the committed
+    `ncu --set full` summary of the SAME workload (cube on), profiles/ncu_full_<round>_cfg<k>.json; None when there is none."""
     p = os.path.join(ROOT, "profiles", "ncu_full_%s_cfg%d.json" % (PROFILE_ROUND, cfg_id))
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tmul = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
     try:
+        tot, tsum, psum, seen = 0.0, 0.0, 0.0, set()
         for k in json.load(open(p)):
-            if k["kernel"].split("(")[0] == kernel:
-                tot = 0.0
+            name = k["kernel"].split("(")[0].split("::")[-1]
+            if name in kernels and name not in seen:
+                seen.add(name)
                 for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     v, u = k[key].split()
                     tot += float(v.replace(",", "")) * mult[u]
+                v, u = k["gpu__time_duration.sum"].split()
+                t = float(v.replace(",", "")) * tmul[u]
                 pipe = k.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
-                return {"traffic": tot, "fp64_pipe_pct": float(pipe.split()[0]) if pipe else None, "file": os.path.relpath(p, ROOT)}
+                tsum += t; psum += t * (float(pipe.split()[0]) if pipe else 0.0)
+        if seen:
+            return {"traffic": tot, "fp64_pipe_pct": psum / tsum if tsum else None, "file": os.path.relpath(p, ROOT), "kernels": sorted(seen)}
     except Exception:
         pass
     return None
@@ -305,7 +312,6 @@ def main():
     cand_total = img.S * img.A * R * B
     # the metric cube (33 B per candidate) is materialised in HBM when it fits comfortably
     want_cube = (not args.no_cube) and cand_rank * 33 <= 100 * (1 << 30)
-    rows_mode = per_rank * img.A * R >= 32768
 
     def solve_step(download):
         if not args.limited:
@@ -341,7 +347,7 @@ def main():
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phases = (("pairs", abi.PHASE_PAIRS), ("grid", abi.PHASE_GRID), ("solve", abi.PHASE_SOLVE), ("totals", abi.PHASE_TOTALS),
-              ("grid_rows_kernel", abi.PHASE_GRID_KERNEL), ("grid_exact_chains", abi.PHASE_GRID_HEAVY))
+              ("grid_prep_cert_kernels", abi.PHASE_GRID_KERNEL), ("grid_exact_chains", abi.PHASE_GRID_HEAVY))
     phase_us = {k: [] for k, _ in phases}
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -411,12 +417,15 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src, peaks = load_peaks()
-        k_name = "k_grid_rows" if rows_mode else "k_grid"
-        k_us = float(np.mean(phase_us["grid_rows_kernel"])) + float(np.mean(phase_us["grid_exact_chains"]))
+        # the sweep = k_scan_prep (exact stop per row) + k_scan_cert (before the stop) + k_scan_lean (after it) with the
+        # exact-chain kernels for uncertified candidates overlapped on a second stream: timed as one phase (CUDA events
+        # around the whole sweep on the sweep's stream)
+        k_names = ["k_scan_prep", "k_scan_cert", "k_scan_lean", "k_grid_list", "k_grid_list_warp"]
+        k_us = float(np.mean(phase_us["grid"]))
         bytes_per_cand = 33.0 if want_cube else 0.0               # 32 B AnalysisMetrics + 1 status byte when the cube is materialised
         alg_bytes = bytes_per_cand * cand_rank + 88.0 * per_rank * img.A + 32.0 * per_rank
         achieved = alg_bytes / (k_us * 1e-6) / 1e9
-        ncu = ncu_summary(k_name, args.config) if want_cube else None
+        ncu = ncu_summary(k_names, args.config) if want_cube else None
         # FP64 view.  Executed FP64-pipe instructions are estimated from the kernel's own work counters: a chain-state
         # update is ~8 FP64-pipe instructions, a certified closed-form tail ~150; the measured pipe utilisation is ncu's
         # sm__inst_executed_pipe_fp64 in profiles/ (quoted below when a summary of this workload is committed).
@@ -435,7 +444,7 @@ def main():
             "cube": "materialised in HBM (33 B/candidate)" if want_cube else "not materialised (winners only)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu["traffic"] if ncu else None, "traffic_source": ncu["file"] if ncu else None,
-                         "peak_source": peak_src, "kernel": k_name + " (+ the exact-chain kernels for uncertified candidates)",
+                         "peak_source": peak_src, "kernel": "candidate sweep: k_scan_prep + k_scan_cert + k_scan_lean (+ exact-chain kernels for uncertified candidates, overlapped)",
                          "kernel_us": k_us, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "north_star's target is 0.60; the sweep is bound by FP64 issue, not by HBM (see fp64)"},
             "fp64": {"bound": "fp64 issue", "achieved": fp64_warp_inst / (k_us * 1e-6) / 1e9, "peak": peak64, "unit": "G thread-inst/s",

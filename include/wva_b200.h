@@ -452,8 +452,9 @@ int wva_grid_counters(const wva_ctx* ctx, uint64_t* steps_executed, uint64_t* st
 
 /* Device self-test of the hoisted-reciprocal double division used by the chain kernels: n operand
  * pairs from a counter-based generator (mode 0: positive a of any exponent / float32-valued b;
- * 1: arbitrary doubles; 2: moderate exponents) are divided both ways; *mismatches counts results
- * that differ bitwise from the plain IEEE operator. */
+ * 1: arbitrary doubles; 2: moderate exponents; 3: float32 operands inside the fast window of the hoisted float32
+ * division; 4: arbitrary float32 bit patterns) are divided both ways; *mismatches counts results that differ
+ * bitwise from the plain IEEE operator. */
 int wva_selftest_division(wva_ctx* ctx, uint64_t seed, uint64_t n, int mode, uint64_t* mismatches);
 
 #ifdef __cplusplus

@@ -150,6 +150,8 @@ struct wva_ctx {
     long long plan_total = 0, plan_maxN = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t gstream = nullptr;      // the candidate sweep has its own stream so it can overlap the pair sizing
+    cudaStream_t gstream2 = nullptr;     // k_scan_lean runs beside k_scan_cert and the exact-chain kernels
+    cudaEvent_t evPrep = nullptr, evLean = nullptr;
     cudaEvent_t evg0 = nullptr, evg1 = nullptr, evJoin = nullptr, evFork = nullptr;
     std::mutex errMutex;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -197,7 +199,7 @@ struct wva_ctx {
 
     // grid
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
-    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch, rowInfo;
+    DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch, rowInfo, rateTab;
     int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0, last_heavy_slice = 0;
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     // solve / totals phases: own event pairs, read lazily (a call that returns nothing to the host does not
@@ -341,6 +343,9 @@ int wva_ctx_create(int device, wva_ctx** out) {
         (e = cudaEventCreate(&ctx->evS0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evS1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evT0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evT1)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->gstream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evPrep, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evLean, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evg0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evg1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess) {
@@ -374,7 +379,7 @@ void wva_ctx_destroy(wva_ctx* ctx) {
                       &ctx->slowCount, &ctx->stepCounter, &ctx->scratch, &ctx->scratchOff, &ctx->pairTabs, &ctx->pairTabOff, &ctx->pairPbuf, &ctx->chosenBuf, &ctx->totals,
                       &ctx->greedyBuf, &ctx->keys, &ctx->bestDev, &ctx->cube, &ctx->status, &ctx->counters,
                       &ctx->gridSlow, &ctx->gridSlowCount, &ctx->faultList, &ctx->faultCount, &ctx->heavyList, &ctx->heavyCost,
-                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->rowInfo, &ctx->ioA, &ctx->ioB,
+                      &ctx->heavyOrder, &ctx->heavyHist, &ctx->pairTab, &ctx->blockSlot, &ctx->listSlot, &ctx->gscratch, &ctx->rowInfo, &ctx->rateTab, &ctx->ioA, &ctx->ioB,
                       &ctx->ioC, &ctx->ioD, &ctx->ioE, &ctx->ioF, &ctx->ioG, &ctx->commTotals, &ctx->commChunk, &ctx->commGather};
     for (DevBuf* b : bufs) b->release();
     ctx->staging.release();
@@ -389,6 +394,8 @@ void wva_ctx_destroy(wva_ctx* ctx) {
     cudaEventDestroy(ctx->evg1);
     cudaEventDestroy(ctx->evJoin);
     cudaEventDestroy(ctx->evFork);
+    cudaEventDestroy(ctx->evPrep); cudaEventDestroy(ctx->evLean);
+    cudaStreamDestroy(ctx->gstream2);
     cudaStreamDestroy(ctx->gstream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -858,8 +865,10 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         const size_t perPairBlocks = (size_t)(gp.n_rchunks > gp.n_bseg ? gp.n_rchunks : gp.n_bseg);
         CK(ctx->blockSlot.ensure((slicePairsMax * perPairBlocks * (scanMode ? 2 : 1) + 1) * sizeof(GridSlot)));
         if (scanMode) CK(ctx->rowInfo.ensure((slicePairsMax * (size_t)r_max + 1) * sizeof(ScanRow)));
+        if (scanMode) CK(ctx->rateTab.ensure((slicePairsMax * (size_t)b_max + 1) * sizeof(float2)));
     }
     gp.row_info = scanMode ? ctx->rowInfo.as<ScanRow>() : nullptr;
+    gp.rate_tab = scanMode ? ctx->rateTab.as<float2>() : nullptr;
     gp.block_slot = ctx->blockSlot.as<GridSlot>();
     const long long stride = 11LL * b_max + 1;
 
@@ -884,6 +893,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         gp.pair_base = sBeg * A;
         int counts[2] = {0, 0};
         int slow = 0, heavy = 0;
+        bool leanPending = false;
         for (int attempt = 0; attempt < 2; ++attempt) {
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
@@ -892,9 +902,16 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
                 // exact stop of every row, then the two halves of the sweep (before / after the stop)
                 k_scan_prep<<<(unsigned)nBlocks, WVA_SCAN_MAXROWS, smem, ctx->gstream>>>(ctx->dsys, gp);
                 LAUNCH_CHECK();
-                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                // k_scan_lean needs the row stops only: it runs on a second stream beside k_scan_cert and, later, beside the
+                // exact-chain kernels (it asks for 46 KB of shared memory it does not use so that at most 4 of its blocks sit on an
+                // SM and a block of the exact-chain kernel still finds registers there)
+                CK(cudaEventRecord(ctx->evPrep, ctx->gstream));
+                CK(cudaStreamWaitEvent(ctx->gstream2, ctx->evPrep, 0));
+                k_scan_lean<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, 46 * 1024, ctx->gstream2>>>(ctx->dsys, gp);
                 LAUNCH_CHECK();
-                k_scan_lean<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, 0, ctx->gstream>>>(ctx->dsys, gp);
+                CK(cudaEventRecord(ctx->evLean, ctx->gstream2));
+                leanPending = true;
+                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
             }
             else if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);
@@ -972,6 +989,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             }
             listSlots += slow;
         }
+        if (leanPending) CK(cudaStreamWaitEvent(ctx->gstream, ctx->evLean, 0));     // join k_scan_lean
         // winners of the slice: the slot that carries a server's minimum key writes its record
         if (nBlocks > 0) {
             const size_t nSlots = scanMode ? 2 * nBlocks : nBlocks;       // k_scan_cert and k_scan_lean each publish one slot per block
@@ -1439,8 +1457,9 @@ __global__ void k_div_selftest(unsigned long long seed, unsigned long long n, in
     unsigned long long bad = 0;
     for (; i < n; i += stride) {
         unsigned long long ra = splitmix64(seed + 2 * i), rb = splitmix64(seed + 2 * i + 1);
-        double a, b;
-        if (mode == 0) {                 // chain-like operands: positive, any exponent; divisor a float32 value
+        double a = 1.0, b = 1.0;
+        if (mode >= 3) {
+        } else if (mode == 0) {                 // chain-like operands: positive, any exponent; divisor a float32 value
             a = __longlong_as_double((long long)(ra & 0x7fffffffffffffffULL));
             float bf = __uint_as_float((unsigned)(rb & 0x7fffffffu));
             b = (double)bf;
@@ -1450,6 +1469,20 @@ __global__ void k_div_selftest(unsigned long long seed, unsigned long long n, in
         } else {                         // moderate exponents: the common case of the chain
             a = __longlong_as_double((long long)((ra & 0x800fffffffffffffULL) | ((0x3ffULL - 40 + (ra >> 52) % 80) << 52)));
             b = __longlong_as_double((long long)((rb & 0x000fffffffffffffULL) | ((0x3ffULL - 20 + (rb >> 52) % 40) << 52)));
+        }
+        if (mode >= 3) {                  // float32: div_hoisted_f32 against the plain operator
+            float af, bf;
+            if (mode == 3) {              // exponents 2^-67 .. 2^66: the fast window [2^-60, 2^60] and both of its edges, both signs
+                af = __uint_as_float((unsigned)(ra & 0x807fffffu) | ((unsigned)(60u + (ra >> 40) % 134u) << 23));
+                bf = __uint_as_float((unsigned)(rb & 0x807fffffu) | ((unsigned)(60u + (rb >> 40) % 134u) << 23));
+            } else {                      // any bit patterns: zeros, subnormals, Inf, NaN, extreme exponents
+                af = __uint_as_float((unsigned)ra); bf = __uint_as_float((unsigned)rb);
+            }
+            const float reff = af / bf;
+            const float gotf = div_hoisted_f32(af, bf, rcp_refined_f32(bf), f32_div_window(bf));
+            const bool samef = (__float_as_uint(reff) == __float_as_uint(gotf)) || (reff != reff && gotf != gotf);
+            if (!samef) ++bad;
+            continue;
         }
         double ref = a / b;
         double got = divisor_in_window(b) ? div_hoisted(a, b, rcp_refined(b)) : a / b;

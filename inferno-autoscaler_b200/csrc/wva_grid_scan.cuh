@@ -222,7 +222,12 @@ k_scan_prep(DevSystem sys, GridParams gp) {
         const double d = (double)rt;
         const double y = rcp_refined(d);
         rateD[i] = d; rcp[i] = y;
-        if (k.rBeg == 1) gtab[i] = make_double2(d, y);          // one block per pair publishes the table
+        if (k.rBeg == 1) {                                       // one block per pair publishes the tables
+            gtab[i] = make_double2(d, y);
+            // RateRange.Max (queueanalyzer.go:116-118) and RateTargetTPS (:231-234, :246) of batch size i + 1
+            const float rateMax = (rt * (1.0f - WVA_EPSILON)) * 1000.0f;
+            gp.rate_tab[(size_t)k.pairSlice * B + i] = make_float2(rateMax, ((rateMax / 1000.0f) * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f);
+        }
         if (!(rt > 0.0f) || !(rt < CUDART_INF_F)) atomicMin(&sh_nGood, i);
     }
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
@@ -239,34 +244,52 @@ k_scan_prep(DevSystem sys, GridParams gp) {
     if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&gp.counters[0], steps);
 }
 
-// metrics, feasibility and key of one analysed candidate from its float32 statistics; stores cube + status
+// Pair- and row-invariant parts of a candidate's float32 epilogue (QueueAnalyzer.Analyze after the Solve,
+// queueanalyzer.go:152-173, EffectiveConcurrency :296-302): the divisors of the two divisions that do not depend on
+// the batch size are inverted once (div_hoisted_f32: same instruction sequence as nvcc's `/`, reciprocal hoisted).
+struct ScanPairCtx {
+    float base, den, yDen, d1, gamma, alpha, beta; bool denOk, inZero;
+    float sloTTFT, sloITL, sloTPS;
+};
+__device__ __forceinline__ ScanPairCtx scan_pair_ctx(const GridServer& gs) {
+    ScanPairCtx pc;
+    const float tokens = (float)(gs.outTok - 1);
+    const float at = gs.sp.alpha * tokens;
+    pc.base = gs.sp.gamma + at;
+    pc.d1 = gs.sp.delta * (float)gs.inTok;
+    const float d2 = gs.sp.beta * tokens;
+    pc.den = pc.d1 + d2;
+    pc.yDen = rcp_refined_f32(pc.den); pc.denOk = f32_div_window(pc.den);
+    pc.gamma = gs.sp.gamma; pc.alpha = gs.sp.alpha; pc.beta = gs.sp.beta; pc.inZero = gs.inTok == 0;
+    pc.sloTTFT = gs.sloTTFT; pc.sloITL = gs.sloITL; pc.sloTPS = gs.sloTPS;
+    return pc;
+}
 struct ScanRowCtx {                // row constants
     float rate, lambda; unsigned long long rowKey; bool valueOk, repOk;
     wva_metrics* rowCube; unsigned char* rowStatus;
 };
-__device__ __forceinline__ void scan_finish(const GridServer& gs, const ScanRowCtx& rc, const SolveStats& so, const int n, const float rateMax,
-                                            unsigned long long& bestKey, float& bestItl, float& bestTtft, float& bestRho) {
-    const int b = n + 1;
-    const float effConc = effective_concurrency(so.avgServTime, gs.sp, gs.inTok, gs.outTok, b);
-    float rho = so.avgNumInServers / (float)b;
-    if (!(rho > 0.0f && rho <= 1.0f)) rho = go_minf(go_maxf(rho, 0.0f), 1.0f);      // the clamp only matters outside (0, 1]
-    const float prefill = prefill_time(gs.sp, gs.inTok, effConc);
-    const float token = decode_time(gs.sp, effConc);
-    const float lamMaxBack = rateMax / 1000.0f;
-    const float rateTPS = (lamMaxBack * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
+// one analysed candidate: metrics from (avgNumInServers, avgNumInSystem, throughput, avgRespTime, avgServTime, avgWaitTime),
+// SLO tests, stores.  Returns feasible.  rateMax / rateTPS come from k_scan_prep's table.
+__device__ __forceinline__ bool scan_finish(const ScanPairCtx& pc, const ScanRowCtx& rc, const SolveStats& so, const int n, const float bF,
+                                            const float rateMax, const float rateTPS, float& itlOut, float& ttftOut, float& rhoOut) {
+    const float num = so.avgServTime - pc.base;
+    const float effN = div_hoisted_f32(num, pc.den, pc.yDen, pc.denOk);
+    const float effConc = (effN > 0.0f && effN <= bF) ? effN : go_minf(go_maxf(effN, 0.0f), bF);      // the clamp only matters outside (0, N]
+    float rho = div_hoisted_f32(so.avgNumInServers, bF, rcp_refined_f32(bF), true);                   // bF = float32(b), 1 <= b <= 8192
+    if (!(rho > 0.0f && rho <= 1.0f)) rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+    const float prefill = pc.inZero ? 0.0f : pc.gamma + pc.d1 * effConc;
+    const float token = pc.alpha + pc.beta * effConc;
     const float ttft = so.avgWaitTime + prefill;
-    const bool feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || token <= gs.sloITL) &&
-                          (!(gs.sloTPS > 0.0f) || rc.rate <= rateTPS) && rc.repOk;
-    if (feasible && rc.valueOk) {
-        const unsigned long long key = rc.rowKey + (unsigned long long)n;
-        if (key < bestKey) { bestKey = key; bestItl = token; bestTtft = ttft; bestRho = rho; }
-    }
+    const bool feasible = (!(pc.sloTTFT > 0.0f) || ttft <= pc.sloTTFT) && (!(pc.sloITL > 0.0f) || token <= pc.sloITL) &&
+                          (!(pc.sloTPS > 0.0f) || rc.rate <= rateTPS) && rc.repOk;
+    itlOut = token; ttftOut = ttft; rhoOut = rho;
     if (rc.rowCube) {
         float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
         c[0] = make_float4(so.throughput * 1000.0f, so.avgRespTime, so.avgWaitTime, so.avgNumInServers);
         c[1] = make_float4(prefill, token, rateMax, rho);
     }
     if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
+    return feasible;
 }
 __device__ __forceinline__ void scan_store_error(const ScanRowCtx& rc, const int n, const int st) {
     if (rc.rowCube) {
@@ -291,6 +314,22 @@ __device__ __forceinline__ ScanRowCtx scan_row_ctx(const GridServer& gs, const G
     rc.rowStatus = gp.status ? gp.status + rowBase : nullptr;
     return rc;
 }
+// Within a row the key grows with the batch size, so the row's best candidate is its FIRST feasible one: the warp keeps
+// (first feasible n, its metrics) per row and compares rows once per row instead of once per candidate.
+struct ScanBest { unsigned long long key; float itl, ttft, rho; };
+__device__ __forceinline__ void scan_row_best(ScanBest& best, bool& rowHas, const ScanRowCtx& rc, const bool feasible, const int n,
+                                              const float itl, const float ttft, const float rho) {
+    if (rowHas) return;                                            // warp-uniform
+    const unsigned m = __ballot_sync(0xffffffffu, feasible && rc.valueOk);
+    if (!m) return;
+    rowHas = true;
+    const int src = __ffs(m) - 1;
+    const int nWin = __shfl_sync(0xffffffffu, n, src);
+    const float i_ = __shfl_sync(0xffffffffu, itl, src), t_ = __shfl_sync(0xffffffffu, ttft, src), r_ = __shfl_sync(0xffffffffu, rho, src);
+    const unsigned long long key = rc.rowKey + (unsigned long long)nWin;
+    if (key < best.key) { best.key = key; best.itl = i_; best.ttft = t_; best.rho = r_; }
+}
+
 // block argmin + counters (shared by k_scan_cert / k_scan_lean); slotBase separates the two kernels' slots
 __device__ __forceinline__ void scan_block_reduce(const DevSystem& sys, const GridParams& gp, const GridServer& gs, const ScanBlock& k, const int slot,
                                                   unsigned long long bestKey, float bestItl, float bestTtft, float bestRho,
@@ -336,52 +375,63 @@ k_scan_lean(DevSystem sys, GridParams gp) {
     GridServer gs;
     if (scan_pair_status(sys, k.s, k.a, gs) != WVA_CAND_OK) return;       // k_scan_prep wrote the pair's status
     __syncthreads();
+    const ScanPairCtx pc = scan_pair_ctx(gs);
     const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
-    const double2* __restrict__ gtab = gp.pair_tab + (size_t)k.pairSlice * B;
+    const float2* __restrict__ rtab = gp.rate_tab + (size_t)k.pairSlice * B;
     const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
-    unsigned long long bestKey = WVA_KEY_NONE, algSteps = 0, okCount = 0;
-    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    ScanBest best; best.key = WVA_KEY_NONE; best.itl = best.ttft = best.rho = 0.0f;
+    unsigned long long algSteps = 0, okCount = 0;
     for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
         const ScanRow row = rowInfo[r - 1];
         if (row.stopB > B) continue;                                // the row never stops: all of it belongs to k_scan_cert
         const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
         const float lambda = rc.lambda;
-        const bool rateOk = rc.rate > 0.0f;
+        const bool rowOk = rc.rate > 0.0f && !(lambda < 0.0f);
+        const int rowErr = !(rc.rate > 0.0f) ? WVA_CAND_ERR_RATE_LE0 : WVA_CAND_ERR_MODEL;
         const double oneMinusSumP = 1.0 - row.exSumP;
         const float inSysF = (float)row.exInSys;
         const float tput = lambda * (1.0f - 0.0f);                  // throughput = lambda * (1 - float32(p[K])), p[K] rounds to 0
         const float respRow = inSysF / tput;                        // avgRespTime: the same for every stopped candidate of the row
+        const float yT = rcp_refined_f32(tput); const bool tOk = f32_div_window(tput);
         // first chunk that lies entirely at or after the stop (the chunk containing the stop is k_scan_cert's)
         const int cFirst = ((row.stopB - 1 + 31) / 32) * 32;
-        for (int c0 = cFirst; c0 < B; c0 += 32) {
+        double bD = (double)(cFirst + lane + 1);
+        float bF = (float)(cFirst + lane + 1);
+        bool rowHas = false;
+        unsigned okRow = 0, algRow = 0;
+        for (int c0 = cFirst; c0 < B; c0 += 32, bD += 32.0, bF += 32.0f) {
             const int n = c0 + lane;
-            if (n >= B) continue;
-            if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides
-                const int k0 = atomicAdd(gp.slow_count, 1);
-                if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(candBase + (size_t)(r - 1) * B + n);
-                continue;
+            bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
+            if (n < B) {
+                if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides
+                    const int k0 = atomicAdd(gp.slow_count, 1);
+                    if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(candBase + (size_t)(r - 1) * B + n);
+                } else {
+                    const float2 rm = rtab[n];
+                    if (!rowOk) scan_store_error(rc, n, rowErr);
+                    else if (rc.rate > rm.x) scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX);
+                    else {
+                        // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no longer
+                        // change; float32(p[K]) < 2^-58 so throughput == lambda
+                        SolveStats so;
+                        const double inServ = row.exInSys + oneMinusSumP * bD;
+                        so.avgNumInServers = (float)inServ;
+                        so.avgNumInSystem = inSysF;
+                        so.throughput = tput;
+                        so.avgRespTime = respRow;
+                        so.avgServTime = div_hoisted_f32(so.avgNumInServers, tput, yT, tOk);
+                        so.avgWaitTime = so.avgRespTime - so.avgServTime;
+                        if (so.avgWaitTime < 0.0f) so.avgWaitTime = 0.0f;
+                        ++okRow; algRow += 22u * (unsigned)(n + 1) + 2u;
+                        feasible = scan_finish(pc, rc, so, n, bF, rm.x, rm.y, itl, ttft, rho);
+                    }
+                }
             }
-            const float rateMax = ((float)gtab[n].x * (1.0f - WVA_EPSILON)) * 1000.0f;
-            if (!rateOk) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_LE0); continue; }
-            if (rc.rate > rateMax) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX); continue; }
-            if (lambda < 0.0f) { scan_store_error(rc, n, WVA_CAND_ERR_MODEL); continue; }
-            // exact: avgNumInServers is captured at i == b (mm1modelstatedependent.go:52-54) from sums that no longer change;
-            // float32(p[K]) < 2^-58 so throughput == lambda
-            SolveStats so;
-            const double inServ = row.exInSys + oneMinusSumP * (double)(n + 1);
-            so.avgNumInServers = (float)inServ;
-            so.avgNumInSystem = inSysF;
-            so.throughput = tput;
-            so.avgRespTime = respRow;
-            so.avgServTime = so.avgNumInServers / so.throughput;
-            so.avgWaitTime = so.avgRespTime - so.avgServTime;
-            if (so.avgWaitTime < 0.0f) so.avgWaitTime = 0.0f;
-            okCount++;
-            algSteps += 2ULL * (unsigned long long)(11 * (n + 1) + 1);
-            scan_finish(gs, rc, so, n, rateMax, bestKey, bestItl, bestTtft, bestRho);
+            scan_row_best(best, rowHas, rc, feasible, n, itl, ttft, rho);
         }
+        okCount += okRow; algSteps += algRow;
     }
-    scan_block_reduce(sys, gp, gs, k, slot, bestKey, bestItl, bestTtft, bestRho, 0ULL, algSteps, okCount, &sh_key, sh_cnt);
+    scan_block_reduce(sys, gp, gs, k, slot, best.key, best.itl, best.ttft, best.rho, 0ULL, algSteps, okCount, &sh_key, sh_cnt);
 }
 
 // ---- the batch sizes before a row's stop: ramp by warp scans + certificate --------------------------------------------
@@ -423,12 +473,15 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
     __syncthreads();
 
-    unsigned long long bestKey = WVA_KEY_NONE, steps = 0, algSteps = 0, okCount = 0;
-    float bestItl = 0.0f, bestTtft = 0.0f, bestRho = 0.0f;
+    const ScanPairCtx pc = scan_pair_ctx(gs);
+    const float2* __restrict__ rtab = gp.rate_tab + (size_t)k.pairSlice * B;
+    ScanBest best; best.key = WVA_KEY_NONE; best.itl = best.ttft = best.rho = 0.0f;
+    unsigned long long steps = 0, algSteps = 0, okCount = 0;
     for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
         const ScanRow row = rowInfo[r - 1];
         const int cEnd = row.stopB > B ? B : ((row.stopB - 1 + 31) / 32) * 32;       // chunks [0, cEnd) are this kernel's
         if (cEnd == 0) continue;
+        bool rowHas = false;
         const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
         const float lambda = rc.lambda;
         const double lam = (double)lambda;
@@ -475,60 +528,62 @@ k_scan_cert(DevSystem sys, GridParams gp) {
                 if (brk) rowBroken = true;
                 steps += 1;
             }
-            if (!inRow) continue;
             // ---- candidate (r, b) ----------------------------------------------------------------------
-            const float rateMax = (rateF[n] * (1.0f - WVA_EPSILON)) * 1000.0f;
-            if (b > row.nGood) {                               // bad table entry: the literal path decides
-                const int k0 = atomicAdd(gp.slow_count, 1);
-                if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(rowBase + n);
-                continue;
-            }
-            if (!rateOk) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_LE0); continue; }
-            if (rc.rate > rateMax) { scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX); continue; }
-            if (lambda < 0.0f) { scan_store_error(rc, n, WVA_CAND_ERR_MODEL); continue; }
-            const int K = 11 * b;
-            SolveStats so;
-            bool certified = false;
-            if (!broken) {
-                if (stoppedLane) {
-                    const double inServ = row.exInSys + oneMinusSumP * (double)b;
-                    finish_stats(so, lambda, inServ, row.exInSys, 0.0f);
-                    certified = true;
-                } else certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
-            }
-            if (!certified) {
-                // exact chain in the list kernels; when that list is full, right here.  (A bad table entry, b > nGood, was
-                // folded into brokenB by k_scan_prep: the list kernels hand those to the literal path.)
-                const int kk = atomicAdd(gp.heavy_count, 1);
-                if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)K; continue; }
-                wva_metrics m;
-                const int st2 = scan_exact_inline(rateF, rateD, rcp, gs, b, rc.rate, tame, m, steps);
-                if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); continue; }
-                if (st2 != WVA_CAND_OK) { scan_store_error(rc, n, st2); continue; }
-                // metrics are final: publish them the way scan_finish would
-                okCount++; algSteps += 2ULL * (unsigned long long)(K + 1);
-                const float rateTPS = ((rateMax / 1000.0f) * (1.0f - WVA_STABILITY_SAFETY)) * 1000.0f;
-                const float ttft = m.avg_wait_time + m.avg_prefill_time;
-                const bool feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || m.avg_token_time <= gs.sloITL) &&
-                                      (!(gs.sloTPS > 0.0f) || rc.rate <= rateTPS) && rc.repOk;
-                if (feasible && rc.valueOk) {
-                    const unsigned long long key = rc.rowKey + (unsigned long long)n;
-                    if (key < bestKey) { bestKey = key; bestItl = m.avg_token_time; bestTtft = ttft; bestRho = m.rho; }
+            bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
+            if (inRow) {
+                const float2 rm = rtab[n];
+                const float rateMax = rm.x;
+                if (b > row.nGood) {                               // bad table entry: the literal path decides
+                    const int k0 = atomicAdd(gp.slow_count, 1);
+                    if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(rowBase + n);
                 }
-                if (rc.rowCube) {
-                    float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
-                    c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
-                    c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+                else if (!rateOk) scan_store_error(rc, n, WVA_CAND_ERR_RATE_LE0);
+                else if (rc.rate > rateMax) scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX);
+                else if (lambda < 0.0f) scan_store_error(rc, n, WVA_CAND_ERR_MODEL);
+                else {
+                    const int K = 11 * b;
+                    SolveStats so;
+                    bool certified = false;
+                    if (!broken) {
+                        if (stoppedLane) {
+                            const double inServ = row.exInSys + oneMinusSumP * (double)b;
+                            finish_stats(so, lambda, inServ, row.exInSys, 0.0f);
+                            certified = true;
+                        } else certified = cert_eval_fast(p, sum, uN, lam, rateD[n], rcp[n], b, K, lambda, so);
+                    }
+                    if (certified) {
+                        okCount++;
+                        algSteps += 2ULL * (unsigned long long)(K + 1);
+                        feasible = scan_finish(pc, rc, so, n, (float)b, rateMax, rm.y, itl, ttft, rho);
+                    } else {
+                        // exact chain in the list kernels; when that list is full, right here
+                        const int kk = atomicAdd(gp.heavy_count, 1);
+                        if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)K; }
+                        else {
+                            wva_metrics m;
+                            const int st2 = scan_exact_inline(rateF, rateD, rcp, gs, b, rc.rate, tame, m, steps);
+                            if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); }
+                            else if (st2 != WVA_CAND_OK) scan_store_error(rc, n, st2);
+                            else {
+                                okCount++; algSteps += 2ULL * (unsigned long long)(K + 1);
+                                ttft = m.avg_wait_time + m.avg_prefill_time; itl = m.avg_token_time; rho = m.rho;
+                                feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
+                                           (!(gs.sloTPS > 0.0f) || rc.rate <= rm.y) && rc.repOk;
+                                if (rc.rowCube) {
+                                    float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
+                                    c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+                                    c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+                                }
+                                if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
+                            }
+                        }
+                    }
                 }
-                if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
-                continue;
             }
-            okCount++;
-            algSteps += 2ULL * (unsigned long long)(K + 1);
-            scan_finish(gs, rc, so, n, rateMax, bestKey, bestItl, bestTtft, bestRho);
+            scan_row_best(best, rowHas, rc, feasible, n, itl, ttft, rho);
         }
     }
-    scan_block_reduce(sys, gp, gs, k, slot, bestKey, bestItl, bestTtft, bestRho, steps, algSteps, okCount, &sh_key, sh_cnt);
+    scan_block_reduce(sys, gp, gs, k, slot, best.key, best.itl, best.ttft, best.rho, steps, algSteps, okCount, &sh_key, sh_cnt);
 }
 
 }  // namespace wva

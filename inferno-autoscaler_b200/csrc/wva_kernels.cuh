@@ -612,6 +612,7 @@ struct GridParams {
     int tail_cap;                    // tail steps a candidate may take inside k_grid before it is deferred
     unsigned long long* heavy_list; float* heavy_cost; int* heavy_count; int heavy_cap;   // deferred (long) chains
     ScanRow* row_info;               // [slice pairs * r_max] k_scan_prep -> k_scan_cert / k_scan_lean
+    float2* rate_tab;                // [slice pairs * b_max] {RateRange.Max, RateTargetTPS} of batch size b (k_scan_prep)
 };
 
 // order-preserving map float -> uint32 (ascending), -0 canonicalised by the caller
@@ -2173,27 +2174,50 @@ __device__ __forceinline__ void greedy_scale(GreedyCtx& c, int s, int slot, long
 // place at least one replica takes it
 __device__ void greedy_allocate_maximally(GreedyCtx& c, const int* list, int n) {
     const int A = c.sys.A;
-    for (int i = 0; i < n; ++i) {
-        const int s = list[i];
-        if (c.sys.srv_model[s] < 0) continue;
-        const int nc = c.g.nCand[s];
-        for (int k0 = 0; k0 < nc; k0 += 32) {
-            const int k = k0 + c.lane;
-            long long maxRep = 0, upr = 0, cur = 0; int t = -1;
-            const int slot = s * A + k;
-            if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; cur = c.g.rep[slot]; }
-            if (t >= 0 && upr > 0) {
-                maxRep = go_divi(c.avail[t], upr);
-                if (cur < maxRep) maxRep = cur;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        // The pass is sequential in `avail`, but everything it reads is known up front: the 32 lanes first pull the
+        // next 32 servers' model / candidate-count words and touch their candidate lines (one exposed memory latency
+        // per 32 servers instead of three dependent ones per server) ...
+        int sMine = -1, ncMine = 0;
+        if (i0 + c.lane < n) {
+            sMine = list[i0 + c.lane];
+            if (c.sys.srv_model[sMine] >= 0) {
+                ncMine = c.g.nCand[sMine];
+                const size_t slot0 = (size_t)sMine * A;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.ctype + slot0));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.upr + slot0));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.rep + slot0));
+                // what greedy_scale reads and rewrites for the server's winner
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.order + slot0));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.cost + slot0));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.value + slot0));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.num_replicas + slot0));
+                if (A > 16) { asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.upr + slot0 + 16)); asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.rep + slot0 + 16)); }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, maxRep > 0);
-            if (m) {
-                if (c.lane == __ffs(m) - 1) {
-                    greedy_scale(c, s, slot, maxRep, cur);
-                    c.avail[t] -= go_muli(maxRep, upr);
+        }
+        const int cnt = (n - i0) < 32 ? (n - i0) : 32;
+        // ... then the servers are served in list order
+        for (int j = 0; j < cnt; ++j) {
+            const int s = __shfl_sync(0xffffffffu, sMine, j);
+            const int nc = __shfl_sync(0xffffffffu, ncMine, j);
+            for (int k0 = 0; k0 < nc; k0 += 32) {
+                const int k = k0 + c.lane;
+                long long maxRep = 0, upr = 0, cur = 0; int t = -1;
+                const int slot = s * A + k;
+                if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; cur = c.g.rep[slot]; }
+                if (t >= 0 && upr > 0) {
+                    maxRep = go_divi(c.avail[t], upr);
+                    if (cur < maxRep) maxRep = cur;
                 }
-                __syncwarp();
-                break;
+                const unsigned m = __ballot_sync(0xffffffffu, maxRep > 0);
+                if (m) {
+                    if (c.lane == __ffs(m) - 1) {
+                        greedy_scale(c, s, slot, maxRep, cur);
+                        c.avail[t] -= go_muli(maxRep, upr);
+                    }
+                    __syncwarp();
+                    break;
+                }
             }
         }
     }
@@ -2532,6 +2556,28 @@ struct GreedyBitmap {
         i = i * 64 + __ffsll((long long)l0[i]) - 1;
         return i;
     }
+    // smallest set rank > p, -1 when there is none
+    __device__ __forceinline__ int nextAfter(int p) const {
+        int w = p >> 6;
+        unsigned long long bits = (p & 63) == 63 ? 0ull : (l0[w] & (~0ull << ((p & 63) + 1)));
+        if (bits) return w * 64 + __ffsll((long long)bits) - 1;
+        int i1 = w >> 6;
+        bits = (w & 63) == 63 ? 0ull : (l1[i1] & (~0ull << ((w & 63) + 1)));
+        if (!bits) {
+            int i2 = i1 >> 6;
+            bits = (i1 & 63) == 63 ? 0ull : (l2[i2] & (~0ull << ((i1 & 63) + 1)));
+            if (!bits) {
+                bits = (i2 & 63) == 63 ? 0ull : (l3[0] & (~0ull << ((i2 & 63) + 1)));
+                if (!bits) return -1;
+                i2 = __ffsll((long long)bits) - 1;
+                bits = l2[i2];
+            }
+            i1 = i2 * 64 + __ffsll((long long)bits) - 1;
+            bits = l1[i1];
+        }
+        w = i1 * 64 + __ffsll((long long)bits) - 1;
+        return w * 64 + __ffsll((long long)l0[w]) - 1;
+    }
     __device__ __forceinline__ void set(int p) {
         const unsigned long long w = l0[p >> 6];
         l0[p >> 6] = w | (1ull << (p & 63));
@@ -2604,8 +2650,14 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
     // state ranks before everything queued (the usual case: the reference re-inserts it at the
     // head of the slice) it is simply evaluated next, reading the server's contiguous candidate
     // records, without going through the queue.
+    // Two upcoming ranks are kept in flight (pf1 = the next minimum, pf2 = the one after): their records are loaded an
+    // iteration or two before they are popped, and as soon as pf1's record is known the lines that a failed placement
+    // walks through (the server's following candidates and their queue positions) are pulled towards L1.  A pop then
+    // runs on registers and L1 hits instead of two or three dependent trips to L2/HBM (measured before: 1 300-1 900
+    // cycles per pop at 10 000 servers).
     int cw = -1; unsigned long long cb = 0;
-    int pfPos = -1; int2 pfNx = make_int2(0, 0); int4 pfRec = make_int4(0, 0, 0, 0);
+    int pf1Pos = -1, pf2Pos = -1;
+    int2 pf1Nx = make_int2(0, 0), pf2Nx = make_int2(0, 0); int4 pf1Rec = make_int4(0, 0, 0, 0), pf2Rec = make_int4(0, 0, 0, 0);
     for (;;) {
         int nUn = 0, more = 0, nextPr = -1;
         const long long t0 = clock64();
@@ -2618,30 +2670,36 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
                 }
                 const int p = cw * 64 + __ffsll((long long)cb) - 1;
                 int4 rec; int2 nx;
-                if (p == pfPos) { rec = pfRec; nx = pfNx; }
+                if (p == pf1Pos) { rec = pf1Rec; nx = pf1Nx; }
                 else { rec = r.rec[p]; nx = r.nextPos[p]; }
-                const unsigned long long rest = cb & (cb - 1);            // without p
-                if (rest) {
-                    pfPos = cw * 64 + __ffsll((long long)rest) - 1;
-                    pfRec = r.rec[pfPos]; pfNx = r.nextPos[pfPos];
-                } else pfPos = -1;
                 int tf = rec.z;
                 const int pr = (tf >> 18) & 0x7f;
                 if (!delayedBestEffort && pr != curPr) {
                     if (curPr < 0) curPr = pr;
-                    else { more = 1; nextPr = pr; break; }
+                    else { more = 1; nextPr = pr; pf1Pos = p; pf1Rec = rec; pf1Nx = nx; break; }
                 }
                 ++nPops;
                 // take p out; m = what the queue holds next (-1: nothing)
+                const unsigned long long rest = cb & (cb - 1);            // without p
                 cb = rest;
                 bm.l0[cw] = rest;
                 int m;
-                if (rest) m = pfPos;
+                if (rest) m = cw * 64 + __ffsll((long long)rest) - 1;
                 else {
                     bm.clear(p);                                          // propagate the empty word upwards
                     m = bm.findMin();
                     if (m >= 0) { cw = m >> 6; cb = bm.l0[cw]; }
                 }
+                // advance the prefetch ring: pf1 <- record of m, pf2 <- record of the rank after m
+                if (m >= 0) {
+                    if (m == pf2Pos) { pf1Pos = m; pf1Rec = pf2Rec; pf1Nx = pf2Nx;
+                                       // pf1's record has been on its way for an iteration: pull its server's walk lines in
+                                       if (!(pf1Rec.z & GREEDY_LAST)) asm volatile("prefetch.global.L1 [%0];" :: "l"(g.cand + pf1Rec.w + 1));
+                                       asm volatile("prefetch.global.L1 [%0];" :: "l"(r.snext + pf1Rec.w)); }
+                    else if (m != pf1Pos) { pf1Pos = m; pf1Rec = r.rec[m]; pf1Nx = r.nextPos[m]; }
+                    const int n2 = bm.nextAfter(m);
+                    if (n2 != pf2Pos) { pf2Pos = n2; if (n2 >= 0) { pf2Rec = r.rec[n2]; pf2Nx = r.nextPos[n2]; } }
+                } else { pf1Pos = pf2Pos = -1; }
                 if (nx.y) r.top[nx.y] = nx.y - p - 1;                     // tie group: p was its lowest occupied rank
                 int state = rec.w, np = nx.x;
                 long long count = (long long)(((unsigned long long)(unsigned)rec.y << 32) | (unsigned)rec.x);
@@ -2678,6 +2736,8 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
                     }
                     bm.set(q);                                            // q > m: the cached word stays the minimum's
                     if ((q >> 6) == cw) cb |= 1ull << (q & 63);
+                    // q > m = pf1Pos; it may now be the rank right after m
+                    if (pf2Pos < 0 || q < pf2Pos) { pf2Pos = q; pf2Rec = r.rec[q]; pf2Nx = r.nextPos[q]; }
                     break;
                 }
             }

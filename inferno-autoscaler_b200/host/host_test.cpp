@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include "wva_host.hpp"
+#include "wva_adapters.hpp"
 
 using namespace wva;
 
@@ -117,6 +118,72 @@ int main() {
             std::printf("{\"scenario\": \"incremental\", \"servers_after_add\": %lld, \"va_after_add\": %lld, \"vb_after_add\": %lld, "
                         "\"removed\": %d, \"removed_again\": %d, \"servers_after_remove\": %lld, \"va_after_remove\": %lld}\n",
                         n2, ra2, rb2, (int)removed, (int)again, n1, ra1);
+        }
+        // delta uploads (system.go:99-171 on the resident image) and Solve -> ReAllocate -> AllocateByType on one System
+        {
+            config::SystemSpec big = optimizerFixture(1200.0f, 200, 80.0f, 500.0f, "A100", 40.0f);
+            config::AcceleratorSpec h2; h2.Name = "H100"; h2.Type = "H100"; h2.Multiplicity = 1; h2.Cost = 100.0f; big.Accelerators.push_back(h2);
+            config::ModelAcceleratorPerfData pd2 = big.Models[0]; pd2.Acc = "H100"; pd2.Decode.Alpha = 7.47f; pd2.Decode.Beta = 0.044f; big.Models.push_back(pd2);
+            for (int i = 0; i < 400; ++i) { config::ServerSpec sv = big.Servers[0]; sv.Name = "s" + std::to_string(i) + ":default"; sv.CurrentAlloc.Load.ArrivalRate = 60.0f + 3.0f * (float)i; big.Servers.push_back(sv); }
+            core::System system(native);
+            const config::OptimizerSpec& os = system.SetFromSpec(big);
+            const long long fullBytes = (long long)system.UploadBytes();
+            solver::Optimizer optimizer(os);
+            manager::Manager manager(system, optimizer);
+            system.Calculate(); manager.Optimize();
+            const long long before = (long long)system.GetServer("s7:default")->Allocation()->NumReplicas();
+            config::ServerSpec s7 = system.GetServer("s7:default")->spec; s7.CurrentAlloc.Load.ArrivalRate = 2400.0f;
+            system.AddServerFromSpec(s7);                                   // replaces the existing server: ONE row goes up
+            const long long deltaBytes = (long long)system.UploadBytes();
+            system.SetCountFromSpec({"A100", 100000});
+            const long long capBytes = (long long)system.UploadBytes();
+            system.Calculate(); manager.Optimize();
+            const long long after = (long long)system.GetServer("s7:default")->Allocation()->NumReplicas();
+            // ReAllocate / Scale after Solve must leave the solved state alone: AllocateByType still works
+            auto ra = system.ReAllocate("s7:default");
+            system.AllocateByType();
+            long long total = 0; for (const auto& kv : system.AllocationByTypeMap()) total += (long long)kv.second.count;
+            std::printf("{\"scenario\": \"delta\", \"full_bytes\": %lld, \"delta_bytes\": %lld, \"capacity_bytes\": %lld, \"replicas_before\": %lld, "
+                        "\"replicas_after\": %lld, \"realloc\": \"%s\", \"by_type_total\": %lld, \"servers\": %zu}\n",
+                        fullBytes, deltaBytes, capBytes, before, after, ra.second.c_str(), total, system.Servers().size());
+        }
+        // the formats either side of the path: ConfigMap-shaped strings in (internal/utils/utils.go:108-311), JSON out.
+        // Inputs: the reference's own chart values for Llama-3.1-8B on L40S (BASELINE config 1).
+        {
+            std::map<std::string, std::map<std::string, std::string>> accCm = {{"L40S", {{"device", "NVIDIA-L40S"}, {"cost", "32.00"}}},
+                                                                                  {"broken", {{"device", "x"}, {"cost", "n/a"}}}};
+            utils::ServiceClass premium; premium.Name = "Premium"; premium.Priority = 1; premium.Data.push_back({"default/default", 24.0, 500.0});
+            config::SystemSpec sd = utils::CreateSystemData(accCm, {premium});
+            utils::AcceleratorProfile prof; prof.Acc = "L40S"; prof.AccCount = 1; prof.MaxBatchSize = 512;
+            prof.DecodeParms = {{"alpha", "22.619"}, {"beta", "0.181"}}; prof.PrefillParms = {{"gamma", "226.19"}, {"delta", "0.018"}};
+            const std::string e1 = utils::AddModelAcceleratorProfileToSystemData(sd, "default/default", prof);
+            utils::AcceleratorProfile bad = prof; bad.DecodeParms = {{"alpha", "abc"}, {"beta", "1"}};
+            const std::string e2 = utils::AddModelAcceleratorProfileToSystemData(sd, "default/default", bad);
+            utils::VariantAutoscaling va; va.Name = "llama"; va.Namespace = "default"; va.ModelID = "default/default"; va.AcceleratorLabel = "L40S";
+            va.Accelerators.push_back(prof);
+            va.CurrentAlloc.Accelerator = "L40S"; va.CurrentAlloc.NumReplicas = 1; va.CurrentAlloc.MaxBatch = 512; va.CurrentAlloc.VariantCost = "32.00";
+            va.CurrentAlloc.ITLAverage = "NaN"; va.CurrentAlloc.TTFTAverage = ""; va.CurrentAlloc.Load.ArrivalRate = "600"; va.CurrentAlloc.Load.AvgInputTokens = "128.7";
+            va.CurrentAlloc.Load.AvgOutputTokens = "128";
+            utils::AddServerInfoToSystemData(sd, va, "Premium", false);
+            core::System system(native);
+            const config::OptimizerSpec& os = system.SetFromSpec(sd);
+            solver::Optimizer optimizer(os);
+            manager::Manager manager(system, optimizer);
+            system.Calculate(); manager.Optimize();
+            std::vector<wva_grid_best> sweep(system.Servers().size());
+            native.check(wva_analyze_grid(native.get(), 8, 256, sweep.data(), nullptr, nullptr));
+            utils::OptimizedAllocExt ext;
+            const bool ok = utils::CreateOptimizedAllocExt(system, "llama", "default", sweep.data(), &ext);
+            utils::OptimizedAllocExt none;
+            const bool missing = utils::CreateOptimizedAllocExt(system, "nobody", "default", sweep.data(), &none);
+            std::printf("{\"scenario\": \"adapters\", \"accelerators\": %zu, \"err_ok\": \"%s\", \"err_bad\": \"%s\", \"in_tokens\": %d, \"itl_in\": %.9g, "
+                        "\"min_replicas\": %d, \"server_batch\": %d, \"found\": %d, \"missing\": %d, \"solution\": %s, \"optimized\": %s, "
+                        "\"floats\": [\"%s\", \"%s\", \"%s\", \"%s\", \"%s\", \"%s\"]}\n",
+                        sd.Accelerators.size(), e1.c_str(), e2.c_str(), sd.Servers[0].CurrentAlloc.Load.AvgInTokens, sd.Servers[0].CurrentAlloc.ITLAverage,
+                        sd.Servers[0].MinNumReplicas, sd.Servers[0].MaxBatchSize, (int)ok, (int)missing,
+                        utils::ToJSON(system.GenerateSolution()).c_str(), utils::ToJSON(ext).c_str(),
+                        utils::JsonFloat32(1e-7f).c_str(), utils::JsonFloat32(1e21f).c_str(), utils::JsonFloat32(0.1f).c_str(),
+                        utils::JsonFloat32(16777216.0f).c_str(), utils::JsonFloat32(-2.5e-5f).c_str(), utils::JsonFloat32(3.4028235e38f).c_str());
         }
     } catch (const Error& e) {
         std::printf("{\"fatal\": {\"code\": %d, \"message\": \"%s\"}}\n", e.code, e.what());

@@ -125,6 +125,8 @@ struct AllocationByType { std::string name; int64_t count = 0, limit = 0; float 
 class System {
 public:
     explicit System(NativeContext& native) : native_(native) {}
+    // H2D bytes of the last image upload or incremental update (wva_upload_bytes)
+    int64_t UploadBytes() const { return wva_upload_bytes(native_.get()); }
 
     // SetFromSpec (system.go:82-90): interns names, resolves (class, model) targets, uploads the SoA image
     const config::OptimizerSpec& SetFromSpec(const config::SystemSpec& d) {
@@ -165,23 +167,11 @@ public:
         s_model.assign(S, -1); s_arr.assign(S, 0); s_in.assign(S, 0); s_out.assign(S, 0); s_ttft.assign(S, 0); s_itl.assign(S, 0);
         s_tps.assign(S, 0); s_tv.assign(S, 0); s_prio.assign(S, config::DefaultServiceClassPriority); s_minr.assign(S, 0);
         s_mb.assign(S, 0); s_keep.assign(S, 0); s_cacc.assign(S, WVA_ACC_NONE); s_crep.assign(S, 0); s_ccost.assign(S, 0);
+        accIdx_ = accIdx; modelIdx_ = modelIdx; classes_ = classes;
         for (int i = 0; i < S; ++i) {
             auto sv = std::make_shared<Server>();
             sv->spec = srv[serverOrder_[i]]; sv->index = i; sv->system = this;
-            sv->serviceClassName = sv->spec.Class.empty() ? config::DefaultServiceClassName : sv->spec.Class;   // server.go:36-39
-            auto mi = modelIdx.find(sv->spec.Model); s_model[i] = mi == modelIdx.end() ? -1 : mi->second;
-            const auto& ld = sv->spec.CurrentAlloc.Load;
-            s_arr[i] = ld.ArrivalRate; s_in[i] = ld.AvgInTokens; s_out[i] = ld.AvgOutTokens;
-            auto ci = classes.find(sv->serviceClassName);
-            if (ci != classes.end()) {
-                sv->priority = ci->second.first; s_prio[i] = sv->priority;
-                auto ti = ci->second.second.find(sv->spec.Model);
-                if (ti != ci->second.second.end()) { s_tv[i] = 1; s_itl[i] = ti->second.SLO_ITL; s_ttft[i] = ti->second.SLO_TTFT; s_tps[i] = ti->second.SLO_TPS; }
-            }
-            s_minr[i] = sv->spec.MinNumReplicas; s_mb[i] = sv->spec.MaxBatchSize; s_keep[i] = sv->spec.KeepAccelerator ? 1 : 0;
-            const auto& ca = sv->spec.CurrentAlloc.Accelerator;
-            if (ca.empty()) s_cacc[i] = WVA_ACC_NONE; else { auto ai = accIdx.find(ca); s_cacc[i] = ai == accIdx.end() ? WVA_ACC_UNKNOWN : ai->second; }
-            s_crep[i] = (int32_t)sv->spec.CurrentAlloc.NumReplicas; s_ccost[i] = sv->spec.CurrentAlloc.Cost;
+            fillServerRow(*sv, i);
             servers_[serverOrder_[i]] = sv;
         }
         uploadImage(s_keep);
@@ -189,22 +179,52 @@ public:
         return spec_.Optimizer;
     }
 
-    // Incremental updates (system.go:98-171).  The spec is edited and the image rebuilt and re-uploaded (one
-    // packed copy; a delta upload of the touched rows is the obvious refinement).  "replace if it already
-    // exists" and the not-found errors (returned as false) are the reference's.
+    // Incremental updates (system.go:98-171) go into the RESIDENT image: a server's row (54 bytes) or the T capacity
+    // counters cross PCIe, not the image (wva_system_update_servers / wva_system_remove_server / wva_system_set_capacity).
+    // "replace if it already exists" and the not-found errors (returned as false) are the reference's.  Accelerator
+    // changes alter the table layout (A) and rebuild the image.
     void AddServerFromSpec(const config::ServerSpec& s) {
-        config::SystemSpec d = spec_;
         bool found = false;
-        for (auto& e : d.Servers) if (e.Name == s.Name) { e = s; found = true; }
-        if (!found) d.Servers.push_back(s);
-        SetFromSpec(d);
+        for (auto& e : spec_.Servers) if (e.Name == s.Name) { e = s; found = true; }
+        if (!found) spec_.Servers.push_back(s);
+        auto it = servers_.find(s.Name);
+        const int idx = it != servers_.end() ? it->second->index : S_;
+        if (idx == S_) {                                   // append: grow the host arrays by one row
+            serverOrder_.push_back(s.Name);
+            s_model.push_back(-1); s_arr.push_back(0); s_in.push_back(0); s_out.push_back(0); s_ttft.push_back(0); s_itl.push_back(0); s_tps.push_back(0);
+            s_tv.push_back(0); s_prio.push_back(config::DefaultServiceClassPriority); s_minr.push_back(0); s_mb.push_back(0); s_keep.push_back(0);
+            s_cacc.push_back(WVA_ACC_NONE); s_crep.push_back(0); s_ccost.push_back(0);
+            ++S_;
+        }
+        auto sv = std::make_shared<Server>();
+        sv->spec = s; sv->index = idx; sv->system = this;
+        fillServerRow(*sv, idx);
+        servers_[s.Name] = sv;
+        wva_system_soa row = serverRows(idx, 1);
+        int rc = wva_system_update_servers(native_.get(), idx, 1, &row);
+        if (rc == WVA_ECAPACITY) uploadImage(s_keep);      // no spare row left: the whole image goes up again
+        else native_.check(rc);
+        analyzed_ = false; created_ = false;
     }
     bool RemoveServer(const std::string& name) {
-        config::SystemSpec d = spec_;
-        const size_t before = d.Servers.size();
-        for (size_t i = d.Servers.size(); i-- > 0;) if (d.Servers[i].Name == name) d.Servers.erase(d.Servers.begin() + (long)i);
-        if (d.Servers.size() == before) return false;
-        SetFromSpec(d);
+        auto it = servers_.find(name);
+        if (it == servers_.end()) return false;
+        for (size_t i = spec_.Servers.size(); i-- > 0;) if (spec_.Servers[i].Name == name) spec_.Servers.erase(spec_.Servers.begin() + (long)i);
+        const int idx = it->second->index, last = S_ - 1;
+        servers_.erase(it);
+        if (idx != last) {                                 // the last server moves into the freed slot (host arrays in step with the device)
+            const std::string moved = serverOrder_[(size_t)last];
+            serverOrder_[(size_t)idx] = moved; servers_[moved]->index = idx;
+            s_model[idx] = s_model[last]; s_arr[idx] = s_arr[last]; s_in[idx] = s_in[last]; s_out[idx] = s_out[last]; s_ttft[idx] = s_ttft[last];
+            s_itl[idx] = s_itl[last]; s_tps[idx] = s_tps[last]; s_tv[idx] = s_tv[last]; s_prio[idx] = s_prio[last]; s_minr[idx] = s_minr[last];
+            s_mb[idx] = s_mb[last]; s_keep[idx] = s_keep[last]; s_cacc[idx] = s_cacc[last]; s_crep[idx] = s_crep[last]; s_ccost[idx] = s_ccost[last];
+        }
+        serverOrder_.pop_back();
+        s_model.pop_back(); s_arr.pop_back(); s_in.pop_back(); s_out.pop_back(); s_ttft.pop_back(); s_itl.pop_back(); s_tps.pop_back(); s_tv.pop_back();
+        s_prio.pop_back(); s_minr.pop_back(); s_mb.pop_back(); s_keep.pop_back(); s_cacc.pop_back(); s_crep.pop_back(); s_ccost.pop_back();
+        --S_;
+        native_.check(wva_system_remove_server(native_.get(), idx));
+        analyzed_ = false; created_ = false;
         return true;
     }
     void AddAcceleratorFromSpec(const config::AcceleratorSpec& a) {
@@ -223,11 +243,12 @@ public:
         return true;
     }
     void SetCountFromSpec(const config::AcceleratorCount& c) {
-        config::SystemSpec d = spec_;
         bool found = false;
-        for (auto& e : d.Capacity) if (e.Type == c.Type) { e = c; found = true; }
-        if (!found) d.Capacity.push_back(c);
-        SetFromSpec(d);
+        for (auto& e : spec_.Capacity) if (e.Type == c.Type) { e = c; found = true; }
+        if (!found) spec_.Capacity.push_back(c);
+        capacity_[c.Type] = c.Count;
+        for (int t = 0; t < T_; ++t) if (typeNames_[t] == c.Type) type_cap[t] = c.Count;   // a type no accelerator has never matters
+        native_.check(wva_system_set_capacity(native_.get(), type_cap.data()));
     }
     void SetCapacityFromSpec(const std::vector<config::AcceleratorCount>& v) { for (const auto& c : v) SetCountFromSpec(c); }
 
@@ -294,21 +315,24 @@ public:
         analyzed_ = true;
     }
 
-    // CreateAllocation(server, accelerator) for every pair, candidate or not (allocation.go:27-163): the pair
-    // kernel honours Server.GetCandidateAccelerators, so the image goes up once with keepAccelerator cleared,
-    // every pair is sized in one launch, and the real image is restored.  value = cost as CreateAllocation
-    // leaves it (:161) -- the transition penalty belongs to Server.Calculate.
+    // CreateAllocation(server, accelerator) for every pair, candidate or not (allocation.go:27-163): the pair kernel
+    // honours Server.GetCandidateAccelerators, so the image goes to a SECOND context with keepAccelerator cleared and
+    // every pair is sized there in one launch -- the main context keeps its candidates, assignment and totals, so
+    // Solve() -> ReAllocate()/Scale() -> AllocateByType() works as in the reference.  value = cost as
+    // CreateAllocation leaves it (:161) -- the transition penalty belongs to Server.Calculate.
     void createAll() {
         if (created_) return;
         const size_t n = (size_t)S_ * A_;
         created_alloc_.assign(n, nullptr);
         if (n) {
+            if (!scratch_) scratch_.reset(new NativeContext(0));
             std::vector<uint8_t> none((size_t)S_, 0);
-            uploadImage(none);
+            wva_system_soa h = imageView(none);
+            scratch_->check(wva_system_upload(scratch_->get(), &h));
             std::vector<int32_t> acc(n); std::vector<int64_t> rep(n), bat(n); std::vector<float> cost(n), val(n), itl(n), ttft(n), rho(n), arrv(n);
             std::vector<uint8_t> fe(n);
             wva_alloc_soa o{acc.data(), rep.data(), bat.data(), cost.data(), val.data(), itl.data(), ttft.data(), rho.data(), arrv.data()};
-            native_.check(wva_analyze_pairs(native_.get(), &o, fe.data()));
+            scratch_->check(wva_analyze_pairs(scratch_->get(), &o, fe.data()));
             for (size_t i = 0; i < n; ++i) {
                 if (!fe[i]) continue;
                 auto al = std::make_shared<Allocation>();
@@ -317,8 +341,6 @@ public:
                 al->ttft = ttft[i]; al->rho = rho[i]; al->maxArrvRatePerReplica = arrv[i];
                 created_alloc_[i] = al;
             }
-            uploadImage(s_keep);
-            analyzed_ = false;
         }
         created_ = true;
     }
@@ -370,7 +392,7 @@ public:
     NativeContext& native() { return native_; }
 
 private:
-    void uploadImage(const std::vector<uint8_t>& keep) {
+    wva_system_soa imageView(const std::vector<uint8_t>& keep) const {
         wva_system_soa h{};
         h.n_servers = S_; h.n_accels = A_; h.n_models = M_; h.n_types = T_;
         h.acc_cost = acc_cost.data(); h.acc_multiplicity = acc_mult.data(); h.acc_type = acc_type.data(); h.type_capacity = type_cap.data();
@@ -380,8 +402,43 @@ private:
         h.srv_slo_ttft = s_ttft.data(); h.srv_slo_itl = s_itl.data(); h.srv_slo_tps = s_tps.data(); h.srv_target_valid = s_tv.data();
         h.srv_priority = s_prio.data(); h.srv_min_replicas = s_minr.data(); h.srv_max_batch = s_mb.data(); h.srv_keep_acc = keep.data();
         h.srv_cur_acc = s_cacc.data(); h.srv_cur_replicas = s_crep.data(); h.srv_cur_cost = s_ccost.data();
+        return h;
+    }
+    // rows [first, first+count) of the server arrays as a wva_system_soa for wva_system_update_servers
+    wva_system_soa serverRows(int first, int count) const {
+        wva_system_soa h = imageView(s_keep);
+        h.n_servers = count;
+        h.srv_model += first; h.srv_arrival_rpm += first; h.srv_in_tokens += first; h.srv_out_tokens += first; h.srv_slo_ttft += first;
+        h.srv_slo_itl += first; h.srv_slo_tps += first; h.srv_target_valid += first; h.srv_priority += first; h.srv_min_replicas += first;
+        h.srv_max_batch += first; h.srv_keep_acc += first; h.srv_cur_acc += first; h.srv_cur_replicas += first; h.srv_cur_cost += first;
+        return h;
+    }
+    void uploadImage(const std::vector<uint8_t>& keep) {
+        wva_system_soa h = imageView(keep);
         native_.check(wva_system_upload(native_.get(), &h));
     }
+    // one server's row of the SoA image: model index, (class, model) target lookup, priority, current allocation
+    void fillServerRow(Server& sv, int i) {
+        sv.serviceClassName = sv.spec.Class.empty() ? config::DefaultServiceClassName : sv.spec.Class;   // server.go:36-39
+        sv.priority = config::DefaultServiceClassPriority;
+        auto mi = modelIdx_.find(sv.spec.Model); s_model[i] = mi == modelIdx_.end() ? -1 : mi->second;
+        const auto& ld = sv.spec.CurrentAlloc.Load;
+        s_arr[i] = ld.ArrivalRate; s_in[i] = ld.AvgInTokens; s_out[i] = ld.AvgOutTokens;
+        s_tv[i] = 0; s_itl[i] = 0; s_ttft[i] = 0; s_tps[i] = 0; s_prio[i] = config::DefaultServiceClassPriority;
+        auto ci = classes_.find(sv.serviceClassName);
+        if (ci != classes_.end()) {
+            sv.priority = ci->second.first; s_prio[i] = sv.priority;
+            auto ti = ci->second.second.find(sv.spec.Model);
+            if (ti != ci->second.second.end()) { s_tv[i] = 1; s_itl[i] = ti->second.SLO_ITL; s_ttft[i] = ti->second.SLO_TTFT; s_tps[i] = ti->second.SLO_TPS; }
+        }
+        s_minr[i] = sv.spec.MinNumReplicas; s_mb[i] = sv.spec.MaxBatchSize; s_keep[i] = sv.spec.KeepAccelerator ? 1 : 0;
+        const auto& ca = sv.spec.CurrentAlloc.Accelerator;
+        if (ca.empty()) s_cacc[i] = WVA_ACC_NONE; else { auto ai = accIdx_.find(ca); s_cacc[i] = ai == accIdx_.end() ? WVA_ACC_UNKNOWN : ai->second; }
+        s_crep[i] = (int32_t)sv.spec.CurrentAlloc.NumReplicas; s_ccost[i] = sv.spec.CurrentAlloc.Cost;
+    }
+    std::unique_ptr<NativeContext> scratch_;
+    std::map<std::string, int> accIdx_, modelIdx_;
+    std::map<std::string, std::pair<int, std::map<std::string, config::ModelTarget>>> classes_;
     NativeContext& native_;
     config::SystemSpec spec_;
     std::vector<std::string> accNames_, typeNames_, modelNames_, serverOrder_;

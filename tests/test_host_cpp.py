@@ -90,3 +90,38 @@ def test_reconcile_sequence_through_cpp_host(wva, oracle):
     assert inc["vb_after_add"] == int(c2.num_replicas[1])
     assert inc["removed"] == 1 and inc["removed_again"] == 0
     assert inc["servers_after_remove"] == 1 and inc["va_after_remove"] == 43
+
+
+def test_delta_uploads_and_solved_state_through_cpp_host(wva, oracle):
+    """system.go:99-171 on the resident image: replacing one of 401 servers moves one row (54 B), a capacity
+    change moves T counters; ReAllocate after Solve leaves the solved state usable."""
+    d = _run()["delta"]
+    assert d["servers"] == 401
+    assert d["delta_bytes"] == 54 and d["capacity_bytes"] == 16 and d["full_bytes"] > 50 * d["delta_bytes"]
+    assert d["replicas_after"] > d["replicas_before"] >= 1
+    assert d["realloc"] in ("A100", "H100") and d["by_type_total"] > 0
+
+
+def test_adapters_in_and_json_out_through_cpp_host(wva, oracle):
+    """ConfigMap-shaped strings in (internal/utils/utils.go:108-311), AllocationSolution JSON out
+    (pkg/config/types.go:123-143), on the reference's own chart values for Llama-3.1-8B / L40S (BASELINE config 1)."""
+    a = _run()["adapters"]
+    assert a["accelerators"] == 1                      # the accelerator whose cost does not parse is skipped (utils.go:121-125)
+    assert a["err_ok"] == "" and "alpha" in a["err_bad"]
+    assert a["in_tokens"] == 128 and a["itl_in"] == 0 and a["min_replicas"] == 1 and a["server_batch"] == 512
+    assert a["found"] == 1 and a["missing"] == 0
+    sol = a["solution"]["allocations"]["llama:default"]
+    # SURVEY 8c derived vector for this fixture: 600 req/min -> N = 512, 5 replicas, cost 160, itl 23.991173, ttft 243.6568
+    assert sol["accelerator"] == "L40S" and sol["numReplicas"] == 5 and sol["maxBatch"] == 512
+    assert F(sol["cost"]) == F(160.0) and F(sol["itlAverage"]) == F(23.991173) and F(sol["ttftAverage"]) == F(243.6568)
+    assert sol["load"] == {"arrivalRate": 600, "avgInTokens": 128, "avgOutTokens": 128}
+    opt = a["optimized"]
+    assert opt["accelerator"] == "L40S" and opt["numReplicas"] == 5 and opt["maxBatch"] == 512 and F(opt["rho"]) == F(0.012853656)
+    # the sweep's winner for the same server against the oracle
+    img = wva.synth.config1()
+    best, _, _, _ = oracle.analyze_grid(img, 8, 256, want_cube=False)
+    sw = opt["sweep"]
+    assert (sw["numReplicas"], sw["maxBatch"]) == (int(best["replicas"][0]), int(best["batch"][0]))
+    assert F(sw["itlAverage"]) == best["itl"][0] and F(sw["ttftAverage"]) == best["ttft"][0] and F(sw["cost"]) == best["cost"][0]
+    # encoding/json float32 formatting: shortest round-trip digits, exponent form below 1e-6 and from 1e21
+    assert a["floats"] == ["1e-7", "1e+21", "0.1", "16777216", "-0.000025", "3.4028235e+38"]

@@ -21,6 +21,10 @@ def test_division_selftest(ctx):
     """div_hoisted(a, b, rcp_refined(b)) == a / b bitwise (the hoisted-reciprocal division of the chain)."""
     for mode in (0, 1, 2):
         assert ctx.selftest_division(1234 + mode, 200_000_000, mode) == 0, mode
+    # float32: the hoisted-reciprocal division of the sweep's epilogue (rows share the divisor lambda, pairs share the
+    # EffectiveConcurrency denominator) against the plain operator: inside its fast window and on arbitrary bit patterns
+    for mode in (3, 4):
+        assert ctx.selftest_division(4321 + mode, 2_000_000_000, mode) == 0, mode
 
 
 def test_queue_analyze_matches_oracle(wva, oracle, ctx):

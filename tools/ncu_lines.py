@@ -25,10 +25,13 @@ for l in dis:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l):
         lines.append((cur, l.split("*/", 1)[1].strip()))
-rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + (sys.argv[5] if len(sys.argv) > 5 else kname)], capture_output=True, text=True).stdout.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]; ie, smp = h.index("Instructions Executed"), h.index("# Samples")
-sass = [r for r in rows[hi + 1:] if len(r) > ie]
+sass, seen = [], set()
+for r in rows[hi + 1:]:
+    if len(r) > ie and r[0].startswith('0x') and r[0] not in seen:
+        seen.add(r[0]); sass.append(r)
 assert abs(len(sass) - len(lines)) <= 8, (len(sass), len(lines))
 agg, sagg = collections.Counter(), collections.Counter()
 tot = ts = 0
