@@ -902,16 +902,17 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
                 // exact stop of every row, then the two halves of the sweep (before / after the stop)
                 k_scan_prep<<<(unsigned)nBlocks, WVA_SCAN_MAXROWS, smem, ctx->gstream>>>(ctx->dsys, gp);
                 LAUNCH_CHECK();
-                // k_scan_lean needs the row stops only: it runs on a second stream beside k_scan_cert and, later, beside the
-                // exact-chain kernels (it asks for 46 KB of shared memory it does not use so that at most 4 of its blocks sit on an
-                // SM and a block of the exact-chain kernel still finds registers there)
+                // k_scan_cert first (it owns the register file: 128 registers x 512 threads per SM), then k_scan_lean on a second
+                // stream BESIDE the exact-chain kernels that follow on this one: those are a few hundred latency-bound warps,
+                // k_scan_lean is bound by the cube's HBM write.  (k_scan_lean asks for 46 KB of shared memory it does not use so
+                // that at most 4 of its blocks sit on an SM and a block of the exact-chain kernel still finds registers there.)
+                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
                 CK(cudaEventRecord(ctx->evPrep, ctx->gstream));
                 CK(cudaStreamWaitEvent(ctx->gstream2, ctx->evPrep, 0));
                 k_scan_lean<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, 46 * 1024, ctx->gstream2>>>(ctx->dsys, gp);
-                LAUNCH_CHECK();
                 CK(cudaEventRecord(ctx->evLean, ctx->gstream2));
                 leanPending = true;
-                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
             }
             else if (rowsMode) k_grid_rows<<<(unsigned)nBlocks, WVA_ROWS_THREADS, smem, ctx->gstream>>>(ctx->dsys, gp);
             else if (wrowMode) k_grid_wrow<<<(unsigned)nBlocks, WVA_GRID_THREADS, smemW, ctx->gstream>>>(ctx->dsys, gp);

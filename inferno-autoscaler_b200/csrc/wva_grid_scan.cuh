@@ -403,9 +403,8 @@ k_scan_lean(DevSystem sys, GridParams gp) {
             const int n = c0 + lane;
             bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
             if (n < B) {
-                if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides
-                    const int k0 = atomicAdd(gp.slow_count, 1);
-                    if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(candBase + (size_t)(r - 1) * B + n);
+                if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides (listed by k_scan_cert,
+                                                                   // whose lists the host reads before this kernel has finished)
                 } else {
                     const float2 rm = rtab[n];
                     if (!rowOk) scan_store_error(rc, n, rowErr);
@@ -455,6 +454,16 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
     const double2* __restrict__ gtab = gp.pair_tab + (size_t)k.pairSlice * B;
     const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
+    // candidates behind a bad table entry (rate not positive / not finite) in k_scan_lean's part of a row: listed here
+    for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
+        const ScanRow row = rowInfo[r - 1];
+        if (row.nGood >= B || row.stopB > B) continue;
+        const int cFirst = ((row.stopB - 1 + 31) / 32) * 32;
+        for (int n = (cFirst > row.nGood ? cFirst : row.nGood) + lane; n < B; n += 32) {
+            const int k0 = atomicAdd(gp.slow_count, 1);
+            if (k0 < gp.slow_cap) gp.slow_list[k0] = (unsigned long long)(candBase + (size_t)(r - 1) * B + n);
+        }
+    }
     // how far this block's rows reach before their stops (the table is only needed up to there)
     int need = 0;
     for (int rr = threadIdx.x; rr <= k.rEnd - k.rBeg; rr += blockDim.x) {

@@ -2650,14 +2650,8 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
     // state ranks before everything queued (the usual case: the reference re-inserts it at the
     // head of the slice) it is simply evaluated next, reading the server's contiguous candidate
     // records, without going through the queue.
-    // Two upcoming ranks are kept in flight (pf1 = the next minimum, pf2 = the one after): their records are loaded an
-    // iteration or two before they are popped, and as soon as pf1's record is known the lines that a failed placement
-    // walks through (the server's following candidates and their queue positions) are pulled towards L1.  A pop then
-    // runs on registers and L1 hits instead of two or three dependent trips to L2/HBM (measured before: 1 300-1 900
-    // cycles per pop at 10 000 servers).
     int cw = -1; unsigned long long cb = 0;
-    int pf1Pos = -1, pf2Pos = -1;
-    int2 pf1Nx = make_int2(0, 0), pf2Nx = make_int2(0, 0); int4 pf1Rec = make_int4(0, 0, 0, 0), pf2Rec = make_int4(0, 0, 0, 0);
+    int pfPos = -1; int2 pfNx = make_int2(0, 0); int4 pfRec = make_int4(0, 0, 0, 0);
     for (;;) {
         int nUn = 0, more = 0, nextPr = -1;
         const long long t0 = clock64();
@@ -2670,38 +2664,38 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
                 }
                 const int p = cw * 64 + __ffsll((long long)cb) - 1;
                 int4 rec; int2 nx;
-                if (p == pf1Pos) { rec = pf1Rec; nx = pf1Nx; }
+                if (p == pfPos) { rec = pfRec; nx = pfNx; }
                 else { rec = r.rec[p]; nx = r.nextPos[p]; }
+                const unsigned long long rest = cb & (cb - 1);            // without p
+                if (rest) {
+                    pfPos = cw * 64 + __ffsll((long long)rest) - 1;
+                    pfRec = r.rec[pfPos]; pfNx = r.nextPos[pfPos];
+                } else pfPos = -1;
                 int tf = rec.z;
                 const int pr = (tf >> 18) & 0x7f;
                 if (!delayedBestEffort && pr != curPr) {
                     if (curPr < 0) curPr = pr;
-                    else { more = 1; nextPr = pr; pf1Pos = p; pf1Rec = rec; pf1Nx = nx; break; }
+                    else { more = 1; nextPr = pr; break; }
                 }
                 ++nPops;
                 // take p out; m = what the queue holds next (-1: nothing)
-                const unsigned long long rest = cb & (cb - 1);            // without p
                 cb = rest;
                 bm.l0[cw] = rest;
                 int m;
-                if (rest) m = cw * 64 + __ffsll((long long)rest) - 1;
+                if (rest) m = pfPos;
                 else {
                     bm.clear(p);                                          // propagate the empty word upwards
                     m = bm.findMin();
                     if (m >= 0) { cw = m >> 6; cb = bm.l0[cw]; }
                 }
-                // advance the prefetch ring: pf1 <- record of m, pf2 <- record of the rank after m
-                if (m >= 0) {
-                    if (m == pf2Pos) { pf1Pos = m; pf1Rec = pf2Rec; pf1Nx = pf2Nx;
-                                       // pf1's record has been on its way for an iteration: pull its server's walk lines in
-                                       if (!(pf1Rec.z & GREEDY_LAST)) asm volatile("prefetch.global.L1 [%0];" :: "l"(g.cand + pf1Rec.w + 1));
-                                       asm volatile("prefetch.global.L1 [%0];" :: "l"(r.snext + pf1Rec.w)); }
-                    else if (m != pf1Pos) { pf1Pos = m; pf1Rec = r.rec[m]; pf1Nx = r.nextPos[m]; }
-                    const int n2 = bm.nextAfter(m);
-                    if (n2 != pf2Pos) { pf2Pos = n2; if (n2 >= 0) { pf2Rec = r.rec[n2]; pf2Nx = r.nextPos[n2]; } }
-                } else { pf1Pos = pf2Pos = -1; }
                 if (nx.y) r.top[nx.y] = nx.y - p - 1;                     // tie group: p was its lowest occupied rank
                 int state = rec.w, np = nx.x;
+                // a failed placement walks through the server's following candidates: start pulling their lines in now
+                // (one line holds a server's 8 candidate records; fire and forget)
+                if (!(tf & GREEDY_LAST)) {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(g.cand + state + 1));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(r.snext + state + 1));
+                }
                 long long count = (long long)(((unsigned long long)(unsigned)rec.y << 32) | (unsigned)rec.x);
                 for (;;) {
                     if (tf & GREEDY_SKIP) break;                          // no model / GetAccelerator("") == nil
@@ -2736,8 +2730,6 @@ __global__ void __launch_bounds__(32) k_greedy_solve_ranked(DevSystem sys, DevAl
                     }
                     bm.set(q);                                            // q > m: the cached word stays the minimum's
                     if ((q >> 6) == cw) cb |= 1ull << (q & 63);
-                    // q > m = pf1Pos; it may now be the rank right after m
-                    if (pf2Pos < 0 || q < pf2Pos) { pf2Pos = q; pf2Rec = r.rec[q]; pf2Nx = r.nextPos[q]; }
                     break;
                 }
             }
