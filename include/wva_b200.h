@@ -282,7 +282,8 @@ int wva_pairs_commit(wva_ctx* ctx);
  * otherwise the exact chain runs.  Results are identical in every mode.
  *   on = 1 (default): one WARP per (server, accelerator, replicas) row, lanes = 32 consecutive batch sizes:
  *           k_scan_prep finds every row's exact stop, k_scan_cert evaluates the batch sizes before it (ramp
- *           by warp scans + certificate), k_scan_lean the ones after it (frozen exact sums);
+ *           by warp scans + certificate), k_scan_lean the ones after it (frozen exact sums);  on = 33: same with
+ *           k_scan_cert's register allocation for 2 instead of 3 blocks per SM;
  *   on = 0: no certificate, exact chains only (one thread per candidate);
  *   on = 17: round-1 automatic choice: one thread per row (shared sequential ramp) for shards with >= 32 K rows,
  *           one thread per candidate below;  on = 3 / 5 / 9: always one thread per candidate / one thread per

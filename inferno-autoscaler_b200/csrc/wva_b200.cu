@@ -359,7 +359,7 @@ int wva_ctx_create(int device, wva_ctx** out) {
     {
         const void* kernels[] = {(const void*)k_grid, (const void*)k_grid_rows, (const void*)k_grid_wrow, (const void*)k_grid_list,
                                  (const void*)k_grid_list_warp, (const void*)k_pairs_warp, (const void*)k_pairs, (const void*)k_grid_claim,
-                                 (const void*)k_grid_best_init, (const void*)k_scan_prep, (const void*)k_scan_cert, (const void*)k_scan_lean};
+                                 (const void*)k_grid_best_init, (const void*)k_scan_prep, (const void*)k_scan_cert<2>, (const void*)k_scan_cert<3>, (const void*)k_scan_lean};
         if (!std::getenv("WVA_NO_CARVEOUT"))
             for (const void* k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaGetLastError();
@@ -690,7 +690,7 @@ int wva_set_certified_tails(wva_ctx* ctx, int32_t on) {
     ctx->grid_rows = (on & 2) ? 0 : ((on & 4) ? 2 : ((on & 8) ? 3 : 1));
     // bits 1-3 select one of the round-1 kernels explicitly (and switch the scan kernel off); bit 4 (16): round-1
     // automatic choice (k_grid / k_grid_rows by shard size); bit 5 (32): scan kernel tuned for 3 blocks per SM
-    ctx->grid_scan = ((on & (2 | 4 | 8 | 16)) || !(on & 1)) ? 0 : 1;
+    ctx->grid_scan = ((on & (2 | 4 | 8 | 16)) || !(on & 1)) ? 0 : ((on & 32) ? 2 : 1);     // bit 5: k_scan_cert tuned for 2 blocks per SM
     ctx->dsys.cert = ctx->certified;
     return WVA_OK;
 }
@@ -855,7 +855,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         CK(cudaFuncSetAttribute(k_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_grid_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_scan_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_scan_cert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_scan_cert<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_scan_cert<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // k_grid_wrow: the table, then per warp the checkpoints and the quotient buffer of warp_exact
     const size_t smemW = align_up(smem, 16) + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8;
@@ -906,7 +907,8 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
                 // stream BESIDE the exact-chain kernels that follow on this one: those are a few hundred latency-bound warps,
                 // k_scan_lean is bound by the cube's HBM write.  (k_scan_lean asks for 46 KB of shared memory it does not use so
                 // that at most 4 of its blocks sit on an SM and a block of the exact-chain kernel still finds registers there.)
-                k_scan_cert<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                if (ctx->grid_scan == 2) k_scan_cert<2><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                else k_scan_cert<3><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
                 LAUNCH_CHECK();
                 CK(cudaEventRecord(ctx->evPrep, ctx->gstream));
                 CK(cudaStreamWaitEvent(ctx->gstream2, ctx->evPrep, 0));

@@ -139,15 +139,6 @@ __device__ __noinline__ void scan_row_exact(const double* rateD, const double* r
     }
 }
 
-// the sweep's last resort when the deferred list is full: the exact chain right here (out of line: it is never
-// on the common path and must not cost the main loop registers)
-__device__ __noinline__ int scan_exact_inline(const float* rateF, const double* rateD, const double* rcp, const GridServer& gs, int b, float rate,
-                                              bool tame, wva_metrics& m, unsigned long long& steps) {
-    ServTable tb; tb.rateF = rateF; tb.rateD = rateD; tb.rcp = rcp;
-    float rt, dc;
-    return analyze_table(tb, gs, b, rate, tame, 0, m, rt, steps, dc);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // The sweep as three kernels, so that each gets the register allocation (and occupancy) its work needs:
 //
@@ -434,7 +425,10 @@ k_scan_lean(DevSystem sys, GridParams gp) {
 }
 
 // ---- the batch sizes before a row's stop: ramp by warp scans + certificate --------------------------------------------
-__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, 2)
+// MINB: resident blocks per SM the register allocation targets (2: 124 registers, no spills; 3: 80 registers, 36 B of
+// spills, 24 warps per SM) -- both are built, wva_set_certified_tails picks (results identical)
+template <int MINB>
+__global__ void __launch_bounds__(WVA_SCAN_WARPS * 32, MINB)
 k_scan_cert(DevSystem sys, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* rateD = reinterpret_cast<double*>(smem_raw);
@@ -448,9 +442,18 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x;
     if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; sh_need = 0; }
-    GridServer gs;
-    if (scan_pair_status(sys, k.s, k.a, gs) != WVA_CAND_OK) return;
+    // the pair's constants live in shared memory: the main loop would otherwise carry ~30 registers of them
+    __shared__ GridServer sh_gs;
+    __shared__ ScanPairCtx sh_pc;
+    __shared__ int sh_status;
+    if (threadIdx.x == 0) {
+        GridServer g0;
+        sh_status = scan_pair_status(sys, k.s, k.a, g0);
+        if (sh_status == WVA_CAND_OK) { sh_gs = g0; sh_pc = scan_pair_ctx(g0); }
+    }
     __syncthreads();
+    if (sh_status != WVA_CAND_OK) return;
+    const GridServer& gs = sh_gs;
     const size_t candBase = ((size_t)k.pairLocal * R) * (size_t)B;
     const double2* __restrict__ gtab = gp.pair_tab + (size_t)k.pairSlice * B;
     const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
@@ -482,7 +485,7 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     const bool tame = tame_parms(gs.sp, gs.inTok, gs.outTok);
     __syncthreads();
 
-    const ScanPairCtx pc = scan_pair_ctx(gs);
+    const ScanPairCtx& pc = sh_pc;
     const float2* __restrict__ rtab = gp.rate_tab + (size_t)k.pairSlice * B;
     ScanBest best; best.key = WVA_KEY_NONE; best.itl = best.ttft = best.rho = 0.0f;
     unsigned long long steps = 0, algSteps = 0, okCount = 0;
@@ -565,27 +568,11 @@ k_scan_cert(DevSystem sys, GridParams gp) {
                         algSteps += 2ULL * (unsigned long long)(K + 1);
                         feasible = scan_finish(pc, rc, so, n, (float)b, rateMax, rm.y, itl, ttft, rho);
                     } else {
-                        // exact chain in the list kernels; when that list is full, right here
+                        // exact chain in the list kernels; should that list ever be full (it holds 16 M entries), the literal-path
+                        // list takes the candidate (the host re-runs a slice whose literal list overflowed with a larger one)
                         const int kk = atomicAdd(gp.heavy_count, 1);
                         if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)K; }
-                        else {
-                            wva_metrics m;
-                            const int st2 = scan_exact_inline(rateF, rateD, rcp, gs, b, rc.rate, tame, m, steps);
-                            if (st2 < 0) { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); }
-                            else if (st2 != WVA_CAND_OK) scan_store_error(rc, n, st2);
-                            else {
-                                okCount++; algSteps += 2ULL * (unsigned long long)(K + 1);
-                                ttft = m.avg_wait_time + m.avg_prefill_time; itl = m.avg_token_time; rho = m.rho;
-                                feasible = (!(gs.sloTTFT > 0.0f) || ttft <= gs.sloTTFT) && (!(gs.sloITL > 0.0f) || itl <= gs.sloITL) &&
-                                           (!(gs.sloTPS > 0.0f) || rc.rate <= rm.y) && rc.repOk;
-                                if (rc.rowCube) {
-                                    float4* c = reinterpret_cast<float4*>(&rc.rowCube[n]);
-                                    c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
-                                    c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
-                                }
-                                if (rc.rowStatus) rc.rowStatus[n] = (unsigned char)(WVA_CAND_OK | (feasible ? WVA_CAND_FEASIBLE : 0));
-                            }
-                        }
+                        else { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); }
                     }
                 }
             }

@@ -3,7 +3,7 @@
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 600 python tools/grid_ab.py 3 1 17 > gpurun_out/r02d_grid_ab_cfg3.txt 2>&1
+timeout 600 python tools/grid_ab.py 3 1 33 17 > gpurun_out/r02d_grid_ab_cfg3.txt 2>&1
 timeout 300 python tools/grid_ab.py 2 1 17 > gpurun_out/r02d_grid_ab_cfg2.txt 2>&1
 timeout 600 python tools/greedy_stats.py > gpurun_out/r02d_greedy_stats.txt 2>&1
 ( time timeout 1800 python -m pytest tests -m gpu -x -q -s --durations=8 ) > gpurun_out/r02d_pytest.log 2>&1
