@@ -420,6 +420,15 @@ int wva_queue_size(wva_ctx* ctx, int32_t n, const wva_queue_config* cfg,
                    const float* target /*3n*/, float* rates /*3n*/, wva_metrics* metrics,
                    float* achieved /*3n*/, uint8_t* status);
 
+/* The bare queueing model of pkg/analyzer: n_calls consecutive MM1ModelStateDependent.Solve(lambda[i], mu[i]) calls on ONE
+ * model NewMM1ModelStateDependent(K, serv_rate[0..n_rates)) (mm1modelstatedependent.go:15-116, queuemodel.go:27-37).  The
+ * model keeps its state between calls (the validity test reads the previous call's p[0]; invalid calls leave the
+ * statistics of the last valid one).  out[9*i .. 9*i+8] = {isValid, rho, avgRespTime, avgWaitTime, avgServTime,
+ * avgNumInSystem, avgQueueLength, avgNumInServers, throughput} after call i; p_out (may be NULL): the K+1 state
+ * probabilities after the last call. */
+int wva_model_solve(wva_ctx* ctx, int64_t K, const float* serv_rate, int32_t n_rates, int32_t n_calls,
+                    const float* lambda, const float* mu, float* out, double* p_out);
+
 /* ---- instrumentation ----------------------------------------------------- */
 
 /* Kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */

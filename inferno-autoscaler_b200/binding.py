@@ -25,6 +25,7 @@ EXPORTS = [
     "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
     "wva_system_upload_arrays", "wva_analyze_pairs_arrays", "wva_pairs_fetch_arrays", "wva_solve_arrays",
     "wva_system_update_servers", "wva_system_update_models", "wva_system_remove_server", "wva_system_set_capacity", "wva_upload_bytes", "wva_system_dims",
+    "wva_model_solve",
     "wva_comm_unique_id", "wva_comm_init", "wva_comm_destroy", "wva_comm_info", "wva_comm_shard",
     "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx", "wva_group_last_error", "wva_group_upload",
     "wva_group_analyze", "wva_group_pairs_fetch", "wva_group_grid_fetch", "wva_group_solve", "wva_group_allocate_by_type",
@@ -97,6 +98,7 @@ def lib():
         L.wva_upload_bytes.argtypes = [vp]
         L.wva_upload_bytes.restype = i64
         L.wva_system_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.wva_model_solve.argtypes = [vp, i64, abi.f32p, i32, i32, abi.f32p, abi.f32p, abi.f32p, C.POINTER(C.c_double)]
         L.wva_comm_unique_id.argtypes = [vp]
         L.wva_comm_init.argtypes = [vp, vp, i32, i32]
         L.wva_comm_destroy.argtypes = [vp]
@@ -415,6 +417,16 @@ class Context:
         self._ck(lib().wva_queue_size(self._h, n, cfgs.ctypes.data, abi.ptr(targets, C.c_float), abi.ptr(rates, C.c_float),
                                       metrics.ctypes.data, abi.ptr(achieved, C.c_float), abi.ptr(status, C.c_uint8)))
         return rates.reshape(n, 3), metrics, achieved.reshape(n, 3), status
+
+    def model_solve(self, K, serv_rate, lambdas, mus):
+        """MM1ModelStateDependent(K, serv_rate): consecutive Solve(lambda, mu) calls on one model -> (out[n, 9], p[K+1])"""
+        sr = np.ascontiguousarray(serv_rate, dtype=np.float32)
+        lam = np.ascontiguousarray(lambdas, dtype=np.float32); mu = np.ascontiguousarray(mus, dtype=np.float32)
+        out = np.zeros((len(lam), 9), dtype=np.float32)
+        p = np.zeros(int(K) + 1, dtype=np.float64)
+        self._ck(lib().wva_model_solve(self._h, int(K), abi.ptr(sr, C.c_float), len(sr), len(lam), abi.ptr(lam, C.c_float),
+                                       abi.ptr(mu, C.c_float), abi.ptr(out.reshape(-1), C.c_float), p.ctypes.data_as(C.POINTER(C.c_double))))
+        return out, p
 
     # ---- instrumentation ---------------------------------------------------------------
     def launch_count(self):

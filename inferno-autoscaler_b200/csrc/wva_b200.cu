@@ -1877,3 +1877,30 @@ int wva_system_set_capacity(wva_ctx* ctx, const int64_t* type_capacity) {
 }
 
 }  // extern "C"
+
+extern "C" int wva_model_solve(wva_ctx* ctx, int64_t K, const float* serv_rate, int32_t n_rates, int32_t n_calls,
+                               const float* lambda, const float* mu, float* out, double* p_out) {
+    if (!ctx || !serv_rate || !lambda || !mu || !out || K < 0 || n_rates < 1 || n_calls < 0) return fail(ctx, WVA_EINVAL, "bad argument");
+    if (K > (1LL << 28)) return fail(ctx, WVA_EINVAL, "K too large for the materialised model");
+    if (n_calls == 0) return WVA_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->ioA.ensure((size_t)n_rates * 4));
+    CK(ctx->ioB.ensure((size_t)n_calls * 8));
+    CK(ctx->ioC.ensure((size_t)n_calls * 36));
+    CK(ctx->scratch.ensure((size_t)(K + 1) * 8));
+    CK(ctx->faultCount.ensure(4));
+    CK(cudaMemcpyAsync(ctx->ioA.p, serv_rate, (size_t)n_rates * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ioB.p, lambda, (size_t)n_calls * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ioB.as<char>() + (size_t)n_calls * 4, mu, (size_t)n_calls * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->faultCount.p, 0, 4, ctx->stream));
+    k_model_solve<<<1, 32, 0, ctx->stream>>>((long long)K, ctx->ioA.as<float>(), n_rates, n_calls, ctx->ioB.as<float>(),
+                                            ctx->ioB.as<float>() + n_calls, ctx->scratch.as<double>(), ctx->ioC.as<float>(), ctx->faultCount.as<int>());
+    LAUNCH_CHECK();
+    int fault = 0;
+    CK(cudaMemcpyAsync(out, ctx->ioC.p, (size_t)n_calls * 36, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p_out) CK(cudaMemcpyAsync(p_out, ctx->scratch.p, (size_t)(K + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&fault, ctx->faultCount.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (fault) return fail(ctx, WVA_ENONFINITE, "the reference does not terminate on this input (service rate <= 0 or NaN inside mm1modelstatedependent.go:84-89)");
+    return WVA_OK;
+}

@@ -1881,6 +1881,35 @@ __global__ void k_totals_merge(int T, int n_ranks, const unsigned char* __restri
     count[t] = c; cost[t] = k;
 }
 
+// pkg/analyzer's bare model: a sequence of MM1ModelStateDependent.Solve(lambda, mu) calls on ONE model instance
+// NewMM1ModelStateDependent(K, servRate) (mm1modelstatedependent.go:15-116 through QueueModel.Solve, queuemodel.go:27-37).
+// The model keeps p[] between calls -- the validity test reads the PREVIOUS call's p[0] -- and the getters keep the last
+// valid statistics.  Literal algorithm with p[] in global memory, one thread (this is the low-level API, not the path).
+struct ArrayServ { const float* r; __device__ __forceinline__ float rate(long long n) const { return r[n - 1]; } };
+__global__ void k_model_solve(long long K, const float* __restrict__ serv, int nRates, int nCalls, const float* __restrict__ lambda,
+                              const float* __restrict__ mu, double* __restrict__ p, float* __restrict__ out, int* __restrict__ fault) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (long long i = 0; i <= K; ++i) p[i] = 0.0;
+    float st[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // isValid, rho, resp, wait, serv, inSystem, queueLen, inServers, throughput
+    ArrayServ sv; sv.r = serv;
+    unsigned long long steps = 0;
+    for (int c = 0; c < nCalls; ++c) {
+        const float lam = lambda[c], m = mu[c];
+        const float rho = 1.0f - (float)p[0];                              // ComputeRho on the stale p[0]
+        st[1] = rho;
+        if ((rho < 0.0f) || (rho >= (float)K) || (lam < 0.0f) || (m <= 0.0f)) st[0] = 0.0f;
+        else {
+            SolveStats so;
+            if (solve_literal(p, sv, (long long)nRates, K, lam, so, steps)) { *fault = 1; st[0] = 0.0f; }
+            else {
+                st[0] = 1.0f; st[1] = so.rho; st[2] = so.avgRespTime; st[3] = so.avgWaitTime; st[4] = so.avgServTime;
+                st[5] = so.avgNumInSystem; st[6] = so.throughput * so.avgWaitTime; st[7] = so.avgNumInServers; st[8] = so.throughput;
+            }
+        }
+        for (int k = 0; k < 9; ++k) out[9 * c + k] = st[k];
+    }
+}
+
 // RemoveServer (system.go:165-171) on the resident image: the last server's row moves into the freed slot.
 __global__ void k_server_move(DevSystem sys, int from, int to) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;

@@ -330,3 +330,21 @@ def test_sharded_pairs_equal_full(wva, oracle, ctx):
         mask = np.zeros(img.S * A, bool); mask[sl] = True
         assert np.array_equal(pfe[sl], ffe[sl])
         _assert_allocs_equal(part, full, mask)
+
+
+def test_model_solve_sequence_matches_oracle(wva, oracle, ctx):
+    """the bare MM1ModelStateDependent of pkg/analyzer (caller-supplied service rates): a sequence of Solve calls on one
+    model instance, including the stale-p[0] validity rule (queuemodel.go:30) and invalid calls in the middle"""
+    rng = np.random.default_rng(33)
+    for K, n_rates in ((40, 7), (1, 1), (300, 300), (120, 200)):
+        serv = np.sort(rng.uniform(0.05, 2.0, n_rates)).astype(F)
+        lam = np.concatenate([rng.uniform(0.01, 1.5 * serv[-1], 6), [-1.0, 0.3, 0.0, 0.7]]).astype(F)
+        mu = np.concatenate([np.ones(7), [0.0, 1.0, 1.0]]).astype(F)
+        out, p = ctx.model_solve(K, serv, lam, mu)
+        m = oracle.Model(K, serv)
+        for i in range(len(lam)):
+            want = m.solve(float(lam[i]), float(mu[i]))
+            got = dict(zip(oracle._SOLVE_KEYS, out[i]))
+            for key in oracle._SOLVE_KEYS:
+                assert np.float32(got[key]).tobytes() == np.float32(want[key]).tobytes() or (np.isnan(got[key]) and np.isnan(want[key])), (K, i, key)
+        assert p.tobytes() == m.probabilities().tobytes()
