@@ -42,7 +42,7 @@ extern "C" {
 #define WVA_ECUDA      -2   /* CUDA runtime failure (no device, OOM, launch error) */
 #define WVA_ESTATE     -3   /* call order violated (e.g. solve before analyze)     */
 #define WVA_ENOSOLUTION -4  /* "no feasible allocations found" (internal/optimizer/optimizer.go:38-40) */
-#define WVA_ENONFINITE -5   /* a candidate value is NaN: ordering of the greedy solver is undefined  */
+#define WVA_ENONFINITE -5   /* an input on which the reference itself does not terminate (wva_model_solve) */
 
 /* ---- tunables (package vars of the reference; part of the parity contract) */
 #define WVA_MAX_QUEUE_TO_BATCH_RATIO 10      /* pkg/config/defaults.go:18 */

@@ -1227,10 +1227,6 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
                 k_greedy_tie_init<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
                 LAUNCH_CHECK();
             }
-            int flags[2] = {0, 0};                                   // NaN seen, (unused)
-            CK(cudaMemcpyAsync(flags, g.nanFlag, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (flags[0]) return fail(ctx, WVA_ENONFINITE, "a candidate value (or the difference of two) is NaN: the greedy order is undefined");
             ctx->greedy_path = rankable ? 2 : 1;
             if (ctx->greedy_path == 2) {
                 // shared memory: the rank bitmap, plus the ticket pool when a round-robin policy can

@@ -2029,7 +2029,6 @@ __global__ void k_greedy_prepare(DevSystem sys, DevAllocs pairs, const unsigned 
         size_t i = base + a;
         if (!feasible[i]) continue;
         float v = pairs.value[i];
-        if (v != v) atomicExch(g.nanFlag, 1);
         int j = n++;
         // stable insertion sort by cmp.Compare(value)
         while (j > 0 && go_cmpf(pairs.value[base + ord[j - 1]], v) > 0) { ord[j] = ord[j - 1]; --j; }
@@ -2037,14 +2036,9 @@ __global__ void k_greedy_prepare(DevSystem sys, DevAllocs pairs, const unsigned 
     }
     g.nCand[s] = n;
     const int m = sys.srv_model[s];
-    float prev = 0.0f;
     for (int k = 0; k < n; ++k) {
         size_t ai = base + ord[k];
         float v = pairs.value[ai];
-        // the deltas of greedy.go:64-71/:147-153 are differences of neighbours in this order; an
-        // inf-inf makes the order of the reference depend on evaluation order: refuse
-        if (k > 0) { float d = v - prev; if (d != d) atomicExch(g.nanFlag, 1); }
-        prev = v;
         int gi = pairs.acc[ai];
         long long upr = 0; int t = -1;
         if (m >= 0 && gi >= 0) { upr = go_muli(num_instances(sys, m, gi), (long long)sys.acc_multiplicity[gi]); t = sys.acc_type[gi]; }
@@ -2062,6 +2056,7 @@ __global__ void k_greedy_prepare(DevSystem sys, DevAllocs pairs, const unsigned 
 
 // monotone map float32 -> uint32 for cmp.Compare on non-NaN values (-0 and +0 coincide)
 __device__ __forceinline__ unsigned f32_sortable(float f) {
+    if (f != f) return 0u;                       // cmp.Compare: NaN sorts before every number
     f = f + 0.0f;
     unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -2075,7 +2070,9 @@ __device__ __forceinline__ unsigned f32_sortable(float f) {
 __device__ __forceinline__ void greedy_keys(int priority, float delta, float value, int stamp,
                                             unsigned long long& ka, unsigned long long& kb) {
     ka = ((unsigned long long)(unsigned)priority << 32) | (unsigned)~f32_sortable(delta);
-    kb = ((unsigned long long)(unsigned)~f32_sortable(value) << 32) | (unsigned)~((unsigned)stamp + 0x80000000u);
+    // orderFunc looks at the values only when the deltas compare == (greedy.go:78-80): two NaN deltas are "equal" whatever
+    // the values are
+    kb = ((unsigned long long)(delta != delta ? 0u : (unsigned)~f32_sortable(value)) << 32) | (unsigned)~((unsigned)stamp + 0x80000000u);
 }
 
 // 4-ary min-heap on (a, b), structure of arrays so that shared memory is used to the byte
@@ -2446,7 +2443,7 @@ __global__ void k_greedy_states(DevSystem sys, GreedyBufs g, GreedyRank r) {
             const float v = g.cand[i].val;
             const float d = k + 1 < n ? g.cand[i + 1].val - v : 3.40282346638528859811704183484516925e+38f;
             a = ((unsigned long long)(unsigned)sys.srv_priority[s] << 32) | (unsigned)~f32_sortable(d);
-            b = ~f32_sortable(v);
+            b = d != d ? 0u : ~f32_sortable(v);           // NaN deltas compare equal without looking at the values (greedy.go:78-80)
             slot = i;
         }
     }

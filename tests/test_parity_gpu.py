@@ -348,3 +348,31 @@ def test_model_solve_sequence_matches_oracle(wva, oracle, ctx):
             for key in oracle._SOLVE_KEYS:
                 assert np.float32(got[key]).tobytes() == np.float32(want[key]).tobytes() or (np.isnan(got[key]) and np.isnan(want[key])), (K, i, key)
         assert p.tobytes() == m.probabilities().tobytes()
+
+
+@pytest.mark.parametrize("policy", [0, 1, 3])
+def test_solve_greedy_nonfinite_values(wva, oracle, ctx, policy):
+    """costs that overflow float32 make candidate values Inf / NaN (Inf - Inf in TransitionPenalty): the greedy order is
+    cmp.Compare's (NaN lowest; orderFunc's delta == delta test fails for NaN), both solver paths, against the oracle"""
+    img = wva.synth.make_system(240, 4, seed=77, n_types=2, max_pair_batch=64)
+    img.acc_cost[1] = np.float32(3.0e38)                       # cost = acc.Cost * float32(instances * replicas) -> +Inf beyond 1 unit
+    has_cur = img.srv_cur_acc >= 0
+    img.srv_cur_cost[has_cur & (np.arange(img.S) % 3 == 0)] = np.float32(np.inf)
+    ctx.upload(img)
+    pairs, feas = ctx.analyze_pairs()
+    o_pairs, o_feas, _ = oracle.analyze_pairs(img, threads=4)
+    assert np.array_equal(feas, o_feas) and pairs.equal_bits(o_pairs)[0]
+    vals = pairs.value[feas.astype(bool)]
+    assert np.isnan(vals).any() and np.isinf(vals).any()
+    acc_u, ch_u = oracle.solve(img, o_pairs, o_feas, unlimited=True)
+    wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.6)
+    for ranked in (1, 0):
+        ctx.solve_set_ranked(ranked)
+        ctx.upload(img)
+        ctx.analyze_pairs(download=False)
+        acc, chosen = ctx.solve(unlimited=False, policy=policy)
+        w_acc, w_chosen = oracle.solve(img, o_pairs, o_feas, unlimited=False, policy=policy)
+        assert np.array_equal(acc, w_acc), ranked
+        ok, field = chosen.equal_bits(w_chosen)
+        assert ok, (ranked, field)
+    ctx.solve_set_ranked(1)
