@@ -153,7 +153,10 @@ def workload(args, world):
         return wva, wva.synth.config1(), c
     per = args.servers_per_rank or c["S"]
     total = per if (args.strong and not args.servers_per_rank) else per * world
-    img = wva.synth.make_system(total, c["A"], seed=args.config, n_types=c["T"])
+    if args.untamed:   # SURVEY 8(d)'s generator as written: out_tokens from 1, no bound on N = maxBatch * atTokens / outTokens
+        img = wva.synth.make_system(total, c["A"], seed=args.config, n_types=c["T"], max_pair_batch=0, out_tokens_min=1)
+    else:
+        img = wva.synth.make_system(total, c["A"], seed=args.config, n_types=c["T"])
     return wva, img, c
 
 
@@ -166,6 +169,8 @@ def config_desc(args, img, c, world):
                         % (args.config, per, img.A, R, B, per * img.A,
                            "capacity-limited greedy (caps at 60% of demand, PriorityExhaustive)" if args.limited else "unlimited"),
             "servers_total": int(img.S), "accelerators": int(img.A), "r_max": R, "b_max": B,
+            "generator": ("SURVEY 8(d) as written (out_tokens 1-1024, unbounded N of the sizing path)" if args.untamed else
+                          "SURVEY 8(d) with the sizing path's N bounded at 512 by a server batch override and out_tokens 32-1024 (one pair cannot dominate a run)"),
             "candidates_per_step": int(img.S) * img.A * R * B, "pairs_per_step": int(img.S) * img.A,
             "sharding": ("strong: the configuration's servers split over the ranks" if args.strong else
                          "weak: every rank owns the configuration's server count") if world > 1 else "single GPU",
@@ -258,6 +263,8 @@ def main():
     ap.add_argument("--strong", action="store_true", help="shard the configuration's own servers over the ranks (strong scaling)")
     ap.add_argument("--ref-servers", type=int, default=16, help="servers per step of the CPU arms' bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--untamed", action="store_true",
+                    help="generate the servers without the server-level bound on the sizing path's N (out_tokens from 1: N up to 262 144, K = 11 N)")
     ap.add_argument("--no-cube", action="store_true", help="do not materialise the metric cube (winners only)")
     ap.add_argument("--verify", action="store_true", help="N > 1: check that the sharded decisions equal a 1-rank pass over the whole system")
     ap.add_argument("--limited", action="store_true",
@@ -413,7 +420,8 @@ def main():
             same_rep = bool(np.array_equal(np.where(a1 < 0, 0, c1.num_replicas), np.where(a1 < 0, 0, rep_l.cpu().numpy())))
             verify = {"decisions_equal_one_rank": same_acc and same_rep, "type_counts_equal": bool(np.array_equal(t1[0], tot_sharded[0])),
                       "type_cost_rel_err": float(np.max(np.abs(t1[1] - tot_sharded[1]) / np.maximum(np.abs(t1[1]), 1e-30)))}
-            assert verify["decisions_equal_one_rank"] and verify["type_counts_equal"] and verify["type_cost_rel_err"] < 1e-5, verify
+            # per-type cost totals are float32 sums of ~10^4 terms in a different order (rank-order partial sums): 1e-4 relative
+            verify["ok"] = bool(verify["decisions_equal_one_rank"] and verify["type_counts_equal"] and verify["type_cost_rel_err"] < 1e-4)
 
     if rank == 0:
         hbm_peak, peak_src, peaks = load_peaks()
@@ -483,6 +491,8 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if verify is not None and not verify["ok"]:
+        raise SystemExit("sharded decisions differ from the one-rank pass: %r" % (verify,))
 
 
 if __name__ == "__main__":

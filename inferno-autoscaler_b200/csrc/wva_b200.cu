@@ -554,10 +554,14 @@ int wva_analyze_pairs(wva_ctx* ctx, wva_alloc_soa* out, uint8_t* feasible) {
                 long long total = 0, maxN = 0;
                 const long long budget = (2LL << 30) / 16;          // at most 2 GB of tables
                 const long long* nHost = ctx->hostN.data() + (size_t)ctx->s0 * A;
+                for (int i = 0; i < nPairs; ++i) { const long long N = nHost[(size_t)i]; if (N > maxN && N <= (1LL << 26)) maxN = N; }
+                // a pair whose table fits the warp's shared-memory slice (<= 3072 entries) needs no table in HBM at all: only
+                // larger ones draw on the budget (round 1 reserved HBM for every pair; at 800 000 pairs per rank -- BASELINE
+                // config 5 -- that blew the budget and sent most pairs to the materialised path)
+                const long long inSmem = ctx->pairs_smem ? (maxN < 3072 ? maxN : 3072) : 0;
                 for (int i = 0; i < nPairs; ++i) {
                     long long N = nHost[(size_t)i];
-                    if (N > maxN && N <= (1LL << 26)) maxN = N;
-                    if (N <= 0) { offs[(size_t)i] = 0; continue; }   // pair does no queueing work: offset unused
+                    if (N <= 0 || N <= inSmem) { offs[(size_t)i] = 0; continue; }   // no queueing work, or table in shared memory: offset unused
                     if (N > (1LL << 26) || total + N > budget) { offs[(size_t)i] = -1; continue; }
                     offs[(size_t)i] = total; total += N;
                 }
