@@ -362,7 +362,8 @@ k_scan_lean(DevSystem sys, GridParams gp) {
     const int B = gp.b_max, R = gp.r_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = gridDim.x + blockIdx.x;                       // second half of gp.block_slot
-    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; }
+    __shared__ int sh_next;
+    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; sh_next = 0; }
     GridServer gs;
     if (scan_pair_status(sys, k.s, k.a, gs) != WVA_CAND_OK) return;       // k_scan_prep wrote the pair's status
     __syncthreads();
@@ -372,7 +373,12 @@ k_scan_lean(DevSystem sys, GridParams gp) {
     const ScanRow* __restrict__ rowInfo = gp.row_info + (size_t)k.pairSlice * R;
     ScanBest best; best.key = WVA_KEY_NONE; best.itl = best.ttft = best.rho = 0.0f;
     unsigned long long algSteps = 0, okCount = 0;
-    for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
+    // rows are handed out dynamically (a shared counter): their lengths differ by an order of magnitude
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = k.rBeg + atomicAdd(&sh_next, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r > k.rEnd) break;
         const ScanRow row = rowInfo[r - 1];
         if (row.stopB > B) continue;                                // the row never stops: all of it belongs to k_scan_cert
         const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
@@ -390,14 +396,17 @@ k_scan_lean(DevSystem sys, GridParams gp) {
         float bF = (float)(cFirst + lane + 1);
         bool rowHas = false;
         unsigned okRow = 0, algRow = 0;
+        float2 rmNext = (cFirst + lane < B) ? rtab[cFirst + lane] : make_float2(0.0f, 0.0f);     // one chunk ahead of its use
         for (int c0 = cFirst; c0 < B; c0 += 32, bD += 32.0, bF += 32.0f) {
             const int n = c0 + lane;
+            const float2 rmCur = rmNext;
+            if (n + 32 < B) rmNext = rtab[n + 32];
             bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
             if (n < B) {
                 if (n + 1 > row.nGood) {                           // bad table entry: the literal path decides (listed by k_scan_cert,
                                                                    // whose lists the host reads before this kernel has finished)
                 } else {
-                    const float2 rm = rtab[n];
+                    const float2 rm = rmCur;
                     if (!rowOk) scan_store_error(rc, n, rowErr);
                     else if (rc.rate > rm.x) scan_store_error(rc, n, WVA_CAND_ERR_RATE_MAX);
                     else {
@@ -436,12 +445,12 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     float* rateF = reinterpret_cast<float*>(rcp + gp.b_max);
     __shared__ unsigned long long sh_key;
     __shared__ unsigned long long sh_cnt[3];
-    __shared__ int sh_need;
+    __shared__ int sh_need, sh_next;
     const ScanBlock k = scan_block(sys, gp);
     const int B = gp.b_max, R = gp.r_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x;
-    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; sh_need = 0; }
+    if (threadIdx.x == 0) { sh_key = WVA_KEY_NONE; sh_cnt[0] = sh_cnt[1] = sh_cnt[2] = 0; gp.block_slot[slot].key = WVA_KEY_NONE; sh_need = 0; sh_next = 0; }
     // the pair's constants live in shared memory: the main loop would otherwise carry ~30 registers of them
     __shared__ GridServer sh_gs;
     __shared__ ScanPairCtx sh_pc;
@@ -489,11 +498,16 @@ k_scan_cert(DevSystem sys, GridParams gp) {
     const float2* __restrict__ rtab = gp.rate_tab + (size_t)k.pairSlice * B;
     ScanBest best; best.key = WVA_KEY_NONE; best.itl = best.ttft = best.rho = 0.0f;
     unsigned long long steps = 0, algSteps = 0, okCount = 0;
-    for (int r = k.rBeg + warp; r <= k.rEnd; r += WVA_SCAN_WARPS) {
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = k.rBeg + atomicAdd(&sh_next, 1);         // rows handed out dynamically: 1 to 16 chunks each
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r > k.rEnd) break;
         const ScanRow row = rowInfo[r - 1];
         const int cEnd = row.stopB > B ? B : ((row.stopB - 1 + 31) / 32) * 32;       // chunks [0, cEnd) are this kernel's
         if (cEnd == 0) continue;
         bool rowHas = false;
+        float2 rmNext = (lane < B) ? rtab[lane] : make_float2(0.0f, 0.0f);            // one chunk ahead of its use
         const ScanRowCtx rc = scan_row_ctx(gs, gp, k.a, r, candBase);
         const float lambda = rc.lambda;
         const double lam = (double)lambda;
@@ -506,6 +520,8 @@ k_scan_cert(DevSystem sys, GridParams gp) {
         for (int c0 = 0; c0 < cEnd; c0 += 32) {
             const int n = c0 + lane, b = n + 1;
             const bool inRow = n < B;
+            const float2 rm = rmNext;
+            if (n + 32 < B) rmNext = rtab[n + 32];
             const bool stoppedLane = b >= row.stopB;
             double p = 0.0, sum = 0.0, uN = 0.0;
             bool broken = rowBroken || !inRow || b >= row.brokenB || b > row.nGood;
@@ -543,7 +559,6 @@ k_scan_cert(DevSystem sys, GridParams gp) {
             // ---- candidate (r, b) ----------------------------------------------------------------------
             bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
             if (inRow) {
-                const float2 rm = rtab[n];
                 const float rateMax = rm.x;
                 if (b > row.nGood) {                               // bad table entry: the literal path decides
                     const int k0 = atomicAdd(gp.slow_count, 1);
