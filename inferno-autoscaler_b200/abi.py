@@ -141,7 +141,10 @@ class AllocArrays:
             if mask is not None:
                 a, b = a[mask], b[mask]
             if np.dtype(dt) == np.float32:
-                a, b = a.view(np.uint32), b.view(np.uint32)
+                # NaN payloads are not part of the contract: an invalid operation (Inf - Inf) yields 0xFFC00000 on amd64
+                # (the reference's platform) and 0x7FFFFFFF on NVIDIA GPUs; every other value is compared bit for bit
+                both_nan = np.isnan(a) & np.isnan(b)
+                a, b = np.where(both_nan, np.uint32(0), a.view(np.uint32)), np.where(both_nan, np.uint32(0), b.view(np.uint32))
             if not np.array_equal(a, b):
                 return False, name
         return True, None

@@ -558,6 +558,7 @@ k_scan_cert(DevSystem sys, GridParams gp) {
             }
             // ---- candidate (r, b) ----------------------------------------------------------------------
             bool feasible = false; float itl = 0.0f, ttft = 0.0f, rho = 0.0f;
+            int deferK = 0;
             if (inRow) {
                 const float rateMax = rm.x;
                 if (b > row.nGood) {                               // bad table entry: the literal path decides
@@ -582,11 +583,24 @@ k_scan_cert(DevSystem sys, GridParams gp) {
                         okCount++;
                         algSteps += 2ULL * (unsigned long long)(K + 1);
                         feasible = scan_finish(pc, rc, so, n, (float)b, rateMax, rm.y, itl, ttft, rho);
-                    } else {
-                        // exact chain in the list kernels; should that list ever be full (it holds 16 M entries), the literal-path
-                        // list takes the candidate (the host re-runs a slice whose literal list overflowed with a larger one)
-                        const int kk = atomicAdd(gp.heavy_count, 1);
-                        if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)K; }
+                    } else deferK = K;                             // exact chain in the list kernels (appended below, warp-wide)
+                }
+            }
+            // Uncertified candidates go to the exact-chain list as ONE block per warp and chunk, in lane order: such candidates
+            // cluster (the aggregates of a row converge as b grows, so a limit on a float32 rounding boundary makes every large
+            // b of that row ambiguous), and a list warp that gets 32 neighbours of one row runs them with one table, one
+            // lambda and nearly equal trip counts.  Should the list ever be full (16 M entries) the literal-path list takes the
+            // candidate (the host re-runs a slice whose literal list overflowed with a larger one).
+            {
+                const unsigned dm = __ballot_sync(0xffffffffu, deferK != 0);
+                if (dm) {
+                    const int leader = __ffs(dm) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(gp.heavy_count, __popc(dm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (deferK) {
+                        const int kk = base + __popc(dm & ((1u << lane) - 1u));
+                        if (kk < gp.heavy_cap) { gp.heavy_list[kk] = (unsigned long long)(rowBase + n); gp.heavy_cost[kk] = (float)deferK; }
                         else { const int k2 = atomicAdd(gp.slow_count, 1); if (k2 < gp.slow_cap) gp.slow_list[k2] = (unsigned long long)(rowBase + n); }
                     }
                 }
