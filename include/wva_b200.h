@@ -319,15 +319,18 @@ int wva_pair_debug(wva_ctx* ctx, uint64_t* out, int32_t n_pairs);
 int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec,
               int32_t* chosen_acc, wva_alloc_soa* chosen);
 
-/* Tuning (limited-capacity solve): 1 (default) = sort the S*A queue states once and run the
- * sequential pass on a rank bitmap in shared memory; 0 = always the heap kernel.  The library itself
- * falls back to the heap when the bitmap does not fit shared memory (more than ~1.7 M states).
- * Same results either way.  wva_solve_greedy_path reports what the last limited solve ran:
- * 1 heap, 2 ranked queue, 0 none yet. */
+/* Tuning (limited-capacity solve): 2 (default) = static-order scan -- the (server, candidate) pairs are sorted
+ * once by the running maximum of their keys and `allocate` is one linear pass of a warp over that order
+ * (csrc/wva_greedy_scan.cuh); 1 = round 1's ranked queue (states sorted once, the sequential pass on a rank bitmap
+ * in shared memory); 0 = always the heap kernel.  The library itself falls back (2 -> 1 -> 0) when a path's shared
+ * memory does not fit (2: one bit per server; 1: one bit per state, ~1.7 M states) or there are more than 32
+ * accelerators (2).  Same results on every path.  wva_solve_greedy_path reports what the last limited solve ran:
+ * 1 heap, 2 ranked queue, 3 static-order scan, 0 none yet. */
 int wva_solve_set_ranked(wva_ctx* ctx, int32_t on);
 int wva_solve_greedy_path(const wva_ctx* ctx);
-/* Instrumentation of the last ranked-queue solve: {queue pops, placements that did not fit,
- * SM cycles in the queue loop, SM cycles in bestEffort}. */
+/* Instrumentation of the last limited solve.  Ranked queue: {queue pops, placements that did not fit,
+ * SM cycles in the queue loop, SM cycles in bestEffort}; static-order scan: {events, batches | runs popped
+ * from shared-group stacks << 32, SM cycles in the pass, SM cycles in bestEffort}. */
 int wva_solve_stats(wva_ctx* ctx, uint64_t out[4]);
 
 /* Replaces System.AllocateByType (pkg/core/system.go:271-300): per accelerator type

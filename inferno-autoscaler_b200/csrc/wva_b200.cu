@@ -192,8 +192,8 @@ struct wva_ctx {
     DevBuf greedyBuf;
     bool greedy_attr = false;
     int grid_list_warp = 1;     // deferred sweep chains: one warp per chain when the list is short
-    int greedy_ranked = 1;      // 0: always the heap kernel
-    int greedy_path = 0;        // last limited solve: 1 heap, 2 ranked queue
+    int greedy_ranked = 2;      // 2: static-order scan, 1: ranked queue, 0: always the heap kernel
+    int greedy_path = 0;        // last limited solve: 1 heap, 2 ranked queue, 3 static-order scan
     uint64_t greedy_stats[4] = {0, 0, 0, 0};
     unsigned long long* greedy_stats_dev = nullptr;
 
@@ -1169,10 +1169,13 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
         // ranked queue: states sorted by their fixed key (see k_greedy_solve_ranked)
         size_t n2 = GREEDY_TILE;
         while (n2 < nSA) n2 <<= 1;
-        const bool rankable = nSA < (1u << 24) && greedy_bitmap_bytes(nSA, nullptr, nullptr, nullptr) + 4096 <= (size_t)kGreedySmem &&
-                              ctx->greedy_ranked;
+        // static-order scan (wva_greedy_scan.cuh): the default; shared memory holds one bit per server
+        const size_t doneBytes = align_up((nS + 31) / 32 * 4, 16);
+        const bool scannable = nSA < (1u << 24) && A <= 32 && doneBytes + 4096 <= (size_t)kGreedySmem && ctx->greedy_ranked >= 2;
+        const bool rankable = !scannable && nSA < (1u << 24) && greedy_bitmap_bytes(nSA, nullptr, nullptr, nullptr) + 4096 <= (size_t)kGreedySmem &&
+                              ctx->greedy_ranked >= 1;
         size_t o_ka = 0, o_kb = 0, o_ks = 0, o_pos = 0, o_sn = 0, o_rec = 0, o_np = 0, o_ge = 0, o_gb = 0, o_top = 0, o_succ = 0;
-        if (rankable) {
+        if (rankable || scannable) {
             o_ka = take(n2 * 8); o_kb = take(n2 * 4); o_ks = take(n2 * 4); o_pos = take(nSA * 4); o_sn = take(nSA * 4);
             o_rec = take(n2 * 16); o_np = take(n2 * 8); o_ge = take(n2 * 4); o_gb = take(n2 * 4); o_top = take((n2 + 1) * 4); o_succ = take(nS * 4);
         }
@@ -1187,14 +1190,20 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
         g.stats = (unsigned long long*)(b + o_stats);
         g.smemBytes = kGreedySmem;
         GreedyRank gr{};
-        if (rankable) {
+        GreedyScan gsc{};
+        if (rankable || scannable) {
             gr.ka = (unsigned long long*)(b + o_ka); gr.kb = (unsigned*)(b + o_kb); gr.kslot = (unsigned*)(b + o_ks);
             gr.posOf = (unsigned*)(b + o_pos); gr.snext = (int*)(b + o_sn); gr.rec = (int4*)(b + o_rec); gr.nextPos = (int2*)(b + o_np);
             gr.gend = (int*)(b + o_ge); gr.gbeg = (int*)(b + o_gb); gr.top = (int*)(b + o_top); gr.succ = (int*)(b + o_succ); gr.n2 = (unsigned)n2;
+            // the scan path lays its arrays over the ranked queue's
+            gsc.ka = gr.ka; gsc.kb = gr.kb; gsc.kslot = gr.kslot; gsc.posOf = gr.posOf; gsc.runHead = (unsigned char*)(b + o_sn);
+            gsc.ev = gr.rec; gsc.push = gr.nextPos; gsc.gbeg = gr.gbeg; gsc.stackTop = gr.top; gsc.stackBuf = gr.gend;
+            gsc.nEv = g.nanFlag; gsc.n2 = (unsigned)n2;
         }
         if (!ctx->greedy_attr) {
             CK(cudaFuncSetAttribute(k_greedy_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmem));
             CK(cudaFuncSetAttribute(k_greedy_solve_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmem));
+            CK(cudaFuncSetAttribute(k_greedy_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmem));
             ctx->greedy_attr = true;
         }
         int* chosenKey = (int*)(b + o_key);
@@ -1207,9 +1216,10 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
             LAUNCH_CHECK();
             k_greedy_bucket_count<<<(S + 255) / 256, 256, 0, ctx->stream>>>(ctx->dsys, g);
             LAUNCH_CHECK();
-            if (rankable) {
+            if (rankable || scannable) {
                 const unsigned nb = (unsigned)((n2 + 255) / 256), nt = (unsigned)(n2 / GREEDY_TILE);
-                k_greedy_states<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                if (scannable) k_greedy_scan_keys<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gsc);
+                else k_greedy_states<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
                 LAUNCH_CHECK();
                 k_greedy_bitonic_tile<<<nt, 512, 0, ctx->stream>>>(gr, 2u, (unsigned)GREEDY_TILE);
                 LAUNCH_CHECK();
@@ -1225,15 +1235,32 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
                 CK(cudaMemsetAsync(gr.top, 0, (n2 + 1) * 4, ctx->stream));
                 k_greedy_index<<<nb, 256, 0, ctx->stream>>>(gr);
                 LAUNCH_CHECK();
-                k_greedy_tie_groups<<<nb, 256, 0, ctx->stream>>>(gr);
-                LAUNCH_CHECK();
-                k_greedy_records<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
-                LAUNCH_CHECK();
-                k_greedy_tie_init<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
-                LAUNCH_CHECK();
+                if (scannable) {
+                    CK(cudaMemsetAsync(gsc.gbeg, 0xff, n2 * 4, ctx->stream));
+                    k_greedy_scan_groups<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, gsc);
+                    LAUNCH_CHECK();
+                    k_greedy_scan_records<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gsc);
+                    LAUNCH_CHECK();
+                } else {
+                    k_greedy_tie_groups<<<nb, 256, 0, ctx->stream>>>(gr);
+                    LAUNCH_CHECK();
+                    k_greedy_records<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                    LAUNCH_CHECK();
+                    k_greedy_tie_init<<<nb, 256, 0, ctx->stream>>>(ctx->dsys, g, gr);
+                    LAUNCH_CHECK();
+                }
             }
-            ctx->greedy_path = rankable ? 2 : 1;
-            if (ctx->greedy_path == 2) {
+            ctx->greedy_path = scannable ? 3 : rankable ? 2 : 1;
+            if (ctx->greedy_path == 3) {
+                // shared memory: one bit per server (stopped or not), plus the ticket pool of the round-robin policies
+                size_t smem = doneBytes;
+                const bool tickets = spec->saturation_policy == WVA_POLICY_ROUND_ROBIN || spec->saturation_policy == WVA_POLICY_PRIORITY_ROUND_ROBIN;
+                if (tickets) smem = std::min((size_t)kGreedySmem, smem + nS * (sizeof(GreedyTicket) + 4));
+                g.smemBytes = (int)smem;
+                k_greedy_scan<<<1, 32, smem, ctx->stream>>>(ctx->dsys, ctx->pairs, g, gsc, chosenKey, spec->delayed_best_effort ? 1 : 0,
+                                                           spec->saturation_policy);
+            }
+            else if (ctx->greedy_path == 2) {
                 // shared memory: the rank bitmap, plus the ticket pool when a round-robin policy can
                 // use it; whatever is not asked for stays L1 for the record loads
                 size_t smem = align_up(greedy_bitmap_bytes(nSA, nullptr, nullptr, nullptr), 16);
@@ -1278,7 +1305,7 @@ int wva_solve(wva_ctx* ctx, const wva_optimizer_spec* spec, int32_t* chosen_acc,
 
 int wva_solve_set_ranked(wva_ctx* ctx, int32_t on) {
     if (!ctx) return WVA_EINVAL;
-    ctx->greedy_ranked = on ? 1 : 0;
+    ctx->greedy_ranked = on < 0 ? 0 : (on > 2 ? 2 : on);
     return WVA_OK;
 }
 int wva_solve_greedy_path(const wva_ctx* ctx) { return ctx ? ctx->greedy_path : WVA_EINVAL; }

@@ -2196,56 +2196,55 @@ __device__ __forceinline__ void greedy_scale(GreedyCtx& c, int s, int slot, long
     c.chosen[s] = slot;
 }
 
-// allocateMaximally, greedy.go:194-223: lane k looks at candidate k, the first lane that can
-// place at least one replica takes it
+// allocateMaximally, greedy.go:194-223, 32 servers of the list at a time: lane l owns server l and a cursor over its
+// candidates.  Inside this function `available` only shrinks (a server takes maxReplicas * upr <= available), so a
+// candidate without room for one replica now never gets it later and the cursor only moves forward.  The lanes that found
+// a candidate are then served in list order; after each one the lanes waiting on the same accelerator type look again
+// (same candidate first).  The records of the 32 winners are scaled together at the end (greedy.go:208-212).
 __device__ void greedy_allocate_maximally(GreedyCtx& c, const int* list, int n) {
+    const unsigned FULL = 0xffffffffu;
     const int A = c.sys.A;
     for (int i0 = 0; i0 < n; i0 += 32) {
-        // The pass is sequential in `avail`, but everything it reads is known up front: the 32 lanes first pull the
-        // next 32 servers' model / candidate-count words and touch their candidate lines (one exposed memory latency
-        // per 32 servers instead of three dependent ones per server) ...
-        int sMine = -1, ncMine = 0;
+        int s = 0, nc = 0;
         if (i0 + c.lane < n) {
-            sMine = list[i0 + c.lane];
-            if (c.sys.srv_model[sMine] >= 0) {
-                ncMine = c.g.nCand[sMine];
-                const size_t slot0 = (size_t)sMine * A;
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.ctype + slot0));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.upr + slot0));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.rep + slot0));
-                // what greedy_scale reads and rewrites for the server's winner
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.order + slot0));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.cost + slot0));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.value + slot0));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(c.pairs.num_replicas + slot0));
-                if (A > 16) { asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.upr + slot0 + 16)); asm volatile("prefetch.global.L1 [%0];" :: "l"(c.g.rep + slot0 + 16)); }
-            }
+            s = list[i0 + c.lane];
+            if (c.sys.srv_model[s] >= 0) nc = c.g.nCand[s];
         }
-        const int cnt = (n - i0) < 32 ? (n - i0) : 32;
-        // ... then the servers are served in list order
-        for (int j = 0; j < cnt; ++j) {
-            const int s = __shfl_sync(0xffffffffu, sMine, j);
-            const int nc = __shfl_sync(0xffffffffu, ncMine, j);
-            for (int k0 = 0; k0 < nc; k0 += 32) {
-                const int k = k0 + c.lane;
-                long long maxRep = 0, upr = 0, cur = 0; int t = -1;
-                const int slot = s * A + k;
-                if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; cur = c.g.rep[slot]; }
+        const size_t slot0 = (size_t)s * A;
+        int k = 0, t = -1;
+        long long upr = 0, cur = 0;
+        // first candidate from k on with room for at least one replica
+        auto look = [&]() -> bool {
+            for (; k < nc; ++k) {
+                t = c.g.ctype[slot0 + k]; upr = c.g.upr[slot0 + k];
                 if (t >= 0 && upr > 0) {
-                    maxRep = go_divi(c.avail[t], upr);
+                    cur = c.g.rep[slot0 + k];
+                    long long maxRep = go_divi(c.avail[t], upr);
                     if (cur < maxRep) maxRep = cur;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, maxRep > 0);
-                if (m) {
-                    if (c.lane == __ffs(m) - 1) {
-                        greedy_scale(c, s, slot, maxRep, cur);
-                        c.avail[t] -= go_muli(maxRep, upr);
-                    }
-                    __syncwarp();
-                    break;
+                    if (maxRep > 0) return true;
                 }
             }
+            return false;
+        };
+        bool has = look();
+        long long got = 0, gotCur = 0; int gotSlot = -1;
+        for (;;) {
+            const unsigned m = __ballot_sync(FULL, has);
+            if (!m) break;
+            const int f = __ffs(m) - 1;
+            if (c.lane == f) {
+                long long maxRep = go_divi(c.avail[t], upr);
+                if (cur < maxRep) maxRep = cur;
+                got = maxRep; gotCur = cur; gotSlot = (int)slot0 + k;
+                c.avail[t] -= go_muli(maxRep, upr);
+                has = false;
+            }
+            __syncwarp();
+            const int tF = __shfl_sync(FULL, t, f);
+            if (has && t == tF) has = look();
         }
+        if (gotSlot >= 0) greedy_scale(c, s, gotSlot, got, gotCur);
+        __syncwarp();
     }
 }
 
@@ -2257,42 +2256,50 @@ __device__ void greedy_allocate_equally(GreedyCtx& c, const int* list, int n) {
         tk = reinterpret_cast<GreedyTicket*>(c.pool);
         liveIdx = reinterpret_cast<int*>(tk + n);
     } else { tk = c.g.tickets; liveIdx = c.g.liveIdx; }
-    // round 1: every present ticket picks the first candidate with room for one replica
-    // (lane k looks at candidate k), then takes its first replica
+    // round 1: every present ticket picks the first candidate with room for one replica, then takes its first replica.
+    // 32 tickets at a time, as in greedy_allocate_maximally: lane l owns ticket l and a forward-only cursor (`available`
+    // only shrinks here), the lanes that found a candidate are served in list order, and after a ticket took its replica
+    // the lanes waiting on the same type look again.
+    const unsigned FULL = 0xffffffffu;
     int live = 0;
-    for (int i = 0; i < n; ++i) {
-        const int s = list[i];
-        GreedyTicket me; me.upr = 0; me.cur = 0; me.slot = -1; me.got = 0; me.type = -1;
-        int state = 0;                                               // 0 absent, 2 active
-        if (c.sys.srv_model[s] >= 0) {
-            const int nc = c.g.nCand[s];
-            for (int k0 = 0; k0 < nc && state == 0; k0 += 32) {
-                const int k = k0 + c.lane;
-                long long upr = 0; int t = -1;
-                const int slot = s * A + k;
-                if (k < nc) { t = c.g.ctype[slot]; upr = c.g.upr[slot]; }
-                const bool fits = t >= 0 && upr > 0 && c.avail[t] >= upr;
-                const unsigned m = __ballot_sync(0xffffffffu, fits);
-                if (m) {
-                    const int src = __ffs(m) - 1;
-                    me.slot = __shfl_sync(0xffffffffu, slot, src);
-                    me.upr = __shfl_sync(0xffffffffu, upr, src);
-                    me.type = __shfl_sync(0xffffffffu, t, src);
-                    me.cur = c.g.rep[me.slot];
-                    state = 2;
-                }
-            }
-            if (state == 2) {
-                // allocatable = min(available/upr, cur) > 0, with upr > 0
-                if (c.avail[me.type] >= me.upr && me.cur > 0) {
-                    me.got = 1;
-                    __syncwarp();
-                    if (c.lane == 0) { c.avail[me.type] -= me.upr; liveIdx[live] = i; }
-                    ++live;
-                }
-            }
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + c.lane;
+        int s = 0, nc = 0;
+        if (i < n) {
+            s = list[i];
+            if (c.sys.srv_model[s] >= 0) nc = c.g.nCand[s];
         }
-        if (c.lane == 0) tk[i] = me;
+        const size_t slot0 = (size_t)s * A;
+        GreedyTicket me; me.upr = 0; me.cur = 0; me.slot = -1; me.got = 0; me.type = -1;
+        int k = 0, t = -1;
+        long long upr = 0;
+        auto look = [&]() -> bool {
+            for (; k < nc; ++k) {
+                t = c.g.ctype[slot0 + k]; upr = c.g.upr[slot0 + k];
+                if (t >= 0 && upr > 0 && c.avail[t] >= upr) return true;
+            }
+            return false;
+        };
+        bool has = look();
+        bool isLive = false;
+        for (;;) {
+            const unsigned m = __ballot_sync(FULL, has);
+            if (!m) break;
+            const int f = __ffs(m) - 1;
+            if (c.lane == f) {
+                me.slot = (int)slot0 + k; me.upr = upr; me.type = t; me.cur = c.g.rep[slot0 + k];
+                // allocatable = min(available/upr, cur) > 0, with upr > 0
+                if (me.cur > 0) { me.got = 1; c.avail[t] -= upr; isLive = true; }
+                has = false;
+            }
+            __syncwarp();
+            const int tF = __shfl_sync(FULL, t, f);
+            if (has && t == tF) has = look();
+        }
+        const unsigned ml = __ballot_sync(FULL, isLive);
+        if (isLive) liveIdx[live + __popc(ml & ((1u << c.lane) - 1u))] = i;
+        live += __popc(ml);
+        if (i < n) tk[i] = me;
         __syncwarp();
     }
     // later rounds: one replica per live ticket per round, in list order.  A round in which every
@@ -2793,3 +2800,4 @@ __global__ void k_greedy_collect(DevSystem sys, DevAllocs pairs, const int* __re
 }  // namespace wva
 
 #include "wva_grid_scan.cuh"
+#include "wva_greedy_scan.cuh"

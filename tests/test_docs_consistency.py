@@ -13,7 +13,7 @@ def _read(*p):
 
 def test_every_kernel_is_described_in_design():
     src = (_read("inferno-autoscaler_b200", "csrc", "wva_kernels.cuh") + _read("inferno-autoscaler_b200", "csrc", "wva_b200.cu") +
-           _read("inferno-autoscaler_b200", "csrc", "wva_grid_scan.cuh"))
+           _read("inferno-autoscaler_b200", "csrc", "wva_grid_scan.cuh") + _read("inferno-autoscaler_b200", "csrc", "wva_greedy_scan.cuh"))
     kernels = set(re.findall(r"__global__[^;{]*?\b(k_[a-z0-9_]+)\s*\(", src, flags=re.S))
     assert len(kernels) >= 30
     design = _read("DESIGN.md")

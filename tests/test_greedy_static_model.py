@@ -1,0 +1,24 @@
+"""CPU: the static-order form of `allocate` that k_greedy_scan runs (csrc/wva_greedy_scan.cuh) against a literal
+restatement of the reference's sorted slice (greedy.go:107-166) on random cases with heavy key ties."""
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import greedy_static_model as gm
+
+
+def test_static_order_equals_queue():
+    rng = random.Random(11)
+    for r in range(4000):
+        servers, avail = gm.random_case(rng)
+        assert gm.queue_allocate(servers, avail) == gm.static_allocate(servers, avail), (servers, avail)
+
+
+def test_static_order_all_keys_tie():
+    rng = random.Random(12)
+    for r in range(300):
+        S = rng.randint(2, 30)
+        servers = [(1, [(0, rng.randrange(2), rng.randint(1, 5), False) for _ in range(rng.randint(1, 4))]) for _ in range(S)]
+        avail = [rng.randint(0, 30), rng.randint(0, 30)]
+        assert gm.queue_allocate(servers, avail) == gm.static_allocate(servers, avail)

@@ -217,15 +217,15 @@ def test_solve_unlimited_and_totals(wva, oracle, ctx):
 
 @pytest.mark.parametrize("policy", [0, 1, 2, 3])
 @pytest.mark.parametrize("delayed", [False, True])
-@pytest.mark.parametrize("ranked", [1, 0])
+@pytest.mark.parametrize("ranked", [2, 1, 0])
 def test_solve_greedy_policies(wva, oracle, ctx, policy, delayed, ranked):
     img, pairs, feas = _capacity_case(wva, oracle, 52, 500, 6, 3, 0.6)
     ctx.upload(img)
     ctx.analyze_pairs(download=False)
     ctx.solve_set_ranked(ranked)
     acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
-    assert ctx.solve_greedy_path() == (2 if ranked else 1)
-    ctx.solve_set_ranked(1)
+    assert ctx.solve_greedy_path() == ranked + 1
+    ctx.solve_set_ranked(2)
     w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
     assert np.array_equal(acc, w_acc)
     _assert_allocs_equal(chosen, w_chosen)
@@ -249,20 +249,53 @@ def test_solve_greedy_ties(wva, oracle, ctx):
     assert feas.reshape(img.S, img.A).any(axis=1).all() and feas.sum() >= 2 * img.S
     acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
     wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.45)
-    for policy, ranked in ((0, 1), (1, 1), (2, 1), (3, 1), (1, 0), (3, 0)):
+    for policy, ranked in ((0, 2), (1, 2), (2, 2), (3, 2), (0, 1), (1, 1), (2, 1), (3, 1), (1, 0), (3, 0)):
         ctx.upload(img)
         ctx.analyze_pairs(download=False)
         ctx.solve_set_ranked(ranked)
         acc, chosen = ctx.solve(unlimited=False, policy=policy)
         path = ctx.solve_greedy_path()
-        ctx.solve_set_ranked(1)
-        assert path == (2 if ranked else 1)          # ranked: every key ties, the tie-group stacks carry the recency order
+        ctx.solve_set_ranked(2)
+        assert path == ranked + 1                    # scan / ranked: every key ties, the shared-group stacks carry the recency order
         w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, policy=policy)
         assert np.array_equal(acc, w_acc)
         _assert_allocs_equal(chosen, w_chosen)
 
 
-@pytest.mark.parametrize("policy,delayed,ranked", [(1, False, 1), (3, True, 1), (2, False, 1), (0, True, 1), (3, True, 0), (1, False, 0)])
+@pytest.mark.parametrize("A,protos", [(6, 7), (12, 5), (20, 3)])
+def test_solve_greedy_partial_ties(wva, oracle, ctx, A, protos):
+    """classes of identical servers (prototype i % protos) with different priorities: long shared groups whose stacks the
+    static-order scan pops several runs at a time (8, 16 or 32 lanes per run for 6, 12 and 20 accelerators), mixed with
+    unique keys; every policy, both best-effort schedules, all three solver paths against the oracle"""
+    S = 420
+    img = wva.synth.make_system(S, A, seed=91 + A, n_types=3, max_pair_batch=64)
+    for name, _ in wva.abi.SRV_FIELDS:
+        arr = getattr(img, name)
+        for i in range(protos, S):
+            if i % 11 != 0:                       # every 11th server keeps its own (unique) keys
+                arr[i] = arr[i % protos]
+    pairs, feas, _ = oracle.analyze_pairs(img, threads=oracle.hardware_threads())
+    acc_u, ch_u = oracle.solve(img, pairs, feas, unlimited=True)
+    wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.5)
+    for policy in (0, 1, 2, 3):
+        for delayed in (False, True):
+            w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
+            for ranked in (2, 1):
+                ctx.upload(img)
+                ctx.analyze_pairs(download=False)
+                ctx.solve_set_ranked(ranked)
+                acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
+                path = ctx.solve_greedy_path()
+                st = ctx.solve_stats()
+                ctx.solve_set_ranked(2)
+                assert path == ranked + 1
+                assert np.array_equal(acc, w_acc), (policy, delayed, ranked)
+                _assert_allocs_equal(chosen, w_chosen)
+                if ranked == 2:
+                    assert (st[1] >> 32) > 0       # runs did go through the shared-group stacks
+
+
+@pytest.mark.parametrize("policy,delayed,ranked", [(1, False, 2), (3, True, 2), (2, False, 2), (0, True, 2), (3, False, 2), (1, False, 1), (3, True, 1), (2, False, 1), (0, True, 1), (3, True, 0), (1, False, 0)])
 def test_solve_greedy_large(wva, oracle, ctx, policy, delayed, ranked):
     """12 000 servers: the delayed-best-effort queue no longer fits shared memory (global-memory
     heap), the per-priority groups do.  Candidates come from the CUDA path (pair parity is
@@ -277,11 +310,11 @@ def test_solve_greedy_large(wva, oracle, ctx, policy, delayed, ranked):
     ctx.solve_set_ranked(ranked)
     acc, chosen = ctx.solve(unlimited=False, delayed_best_effort=delayed, policy=policy)
     path = ctx.solve_greedy_path()
-    ctx.solve_set_ranked(1)
+    ctx.solve_set_ranked(2)
     w_acc, w_chosen = oracle.solve(img, pairs, feas, unlimited=False, delayed_best_effort=delayed, policy=policy)
     assert np.array_equal(acc, w_acc)
     _assert_allocs_equal(chosen, w_chosen)
-    assert path == (2 if ranked else 1)
+    assert path == ranked + 1
     count, cost = ctx.allocate_by_type()
     assert (count <= img.type_capacity).all()
     assert (acc < 0).any() or policy != 0
@@ -366,7 +399,7 @@ def test_solve_greedy_nonfinite_values(wva, oracle, ctx, policy):
     assert np.isnan(vals).any() and np.isinf(vals).any()
     acc_u, ch_u = oracle.solve(img, o_pairs, o_feas, unlimited=True)
     wva.synth.set_capacity_from_demand(img, ch_u.acc, ch_u.num_replicas, fraction=0.6)
-    for ranked in (1, 0):
+    for ranked in (2, 1, 0):
         ctx.solve_set_ranked(ranked)
         ctx.upload(img)
         ctx.analyze_pairs(download=False)
@@ -375,4 +408,4 @@ def test_solve_greedy_nonfinite_values(wva, oracle, ctx, policy):
         assert np.array_equal(acc, w_acc), ranked
         ok, field = chosen.equal_bits(w_chosen)
         assert ok, (ranked, field)
-    ctx.solve_set_ranked(1)
+    ctx.solve_set_ranked(2)

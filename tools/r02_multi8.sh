@@ -15,10 +15,13 @@ run() {  # N, name, extra args
         bench.py --gpus $n --no-cpu-baseline "$@" > gpurun_out/${TAG}_${name}_n${n}.json 2> gpurun_out/${TAG}_${name}_n${n}.err
   fi
 }
-( time timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/${TAG}_pytest_multi.log 2>&1
-for n in 2 4 8; do run $n weak3 --steps 20 --warmup 5; done
+if [ "${2:-full}" = "full" ]; then
+  ( time timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/${TAG}_pytest_multi.log 2>&1
+  for n in 2 4; do run $n weak3 --steps 20 --warmup 5; done
+  run 1 strong5 --config 5 --strong --no-cube --steps 3 --warmup 3
+fi
+run 8 weak3 --steps 20 --warmup 5
 run 8 strong4 --config 4 --strong --verify --steps 10 --warmup 3
 run 8 strong4lim --config 4 --strong --limited --verify --steps 10 --warmup 3
-run 1 strong5 --config 5 --strong --no-cube --steps 3 --warmup 3
 run 8 strong5 --config 5 --strong --no-cube --verify --steps 5 --warmup 3
 ls -la gpurun_out | grep ${TAG}
