@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--untamed", action="store_true",
                     help="generate the servers without the server-level bound on the sizing path's N (out_tokens from 1: N up to 262 144, K = 11 N)")
     ap.add_argument("--no-cube", action="store_true", help="do not materialise the metric cube (winners only)")
+    ap.add_argument("--stop-and-go", action="store_true", help="diagnostic: the sweep always stops at the host between its kernels (wva_grid_set_fused(0))")
     ap.add_argument("--verify", action="store_true", help="N > 1: check that the sharded decisions equal a 1-rank pass over the whole system")
     ap.add_argument("--limited", action="store_true",
                     help="capacity-constrained assignment (SolveGreedy, PriorityExhaustive): capacities = 60 %% of the "
@@ -295,6 +296,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = binding.Context(local_rank)
+    if args.stop_and_go:
+        ctx.grid_set_fused(False)
     if world > 1:
         D.attach_library_comm(ctx, dev)                    # the collective runs inside the library from here on
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)

@@ -454,6 +454,12 @@ void* wva_stream(const wva_ctx* ctx);
  * sent to the materialised-p[] path. */
 int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap);
 int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal);
+/* Tuning (sweep): when the previous sweep deferred more than 4096 candidates to the exact-chain kernels, the next one
+ * launches all its kernels without stopping at the host in between (the chain kernel reads the list length from device
+ * memory and runs on SMs of its own beside the cube-writing half).  on = 1 (default) / 0 = always stop and go.  Same
+ * results either way.  wva_grid_last_fused: 1 when the last sweep slice ran that way. */
+int wva_grid_set_fused(wva_ctx* ctx, int32_t on);
+int wva_grid_last_fused(const wva_ctx* ctx);
 /* Candidate ids (cube indices relative to the shard) the last sweep slice handed to the exact-chain
  * kernel because their certificate was ambiguous or their tail outlasted tail_cap (at most cap are
  * copied; *n = how many there were).  Test/diagnostic aid: parity tests re-evaluate exactly these. */

@@ -22,7 +22,7 @@ EXPORTS = [
     "wva_analyze_pairs", "wva_pairs_device", "wva_pairs_commit", "wva_pair_steps", "wva_pair_counters", "wva_pair_debug", "wva_analyze_grid",
     "wva_analyze_grid_device", "wva_grid_fetch", "wva_solve", "wva_allocate_by_type", "wva_type_totals_device",
     "wva_solution_time_usec", "wva_queue_analyze", "wva_queue_size", "wva_launch_count", "wva_phase_time_usec",
-    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
+    "wva_grid_counters", "wva_selftest_division", "wva_stream", "wva_grid_set_tail_cap", "wva_grid_list_sizes", "wva_grid_set_fused", "wva_grid_last_fused", "wva_pairs_set_warp_max", "wva_pairs_set_pstore", "wva_solve_set_ranked", "wva_solve_greedy_path", "wva_solve_stats", "wva_type_totals_merge", "wva_set_certified_tails", "wva_analyze", "wva_pairs_fetch", "wva_grid_deferred_fetch",
     "wva_system_upload_arrays", "wva_analyze_pairs_arrays", "wva_pairs_fetch_arrays", "wva_solve_arrays",
     "wva_system_update_servers", "wva_system_update_models", "wva_system_remove_server", "wva_system_set_capacity", "wva_upload_bytes", "wva_system_dims",
     "wva_model_solve",
@@ -88,6 +88,8 @@ def lib():
         L.wva_pairs_fetch.argtypes = [vp, C.POINTER(abi.AllocSoa), abi.u8p]
         L.wva_grid_set_tail_cap.argtypes = [vp, i32]
         L.wva_grid_list_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.wva_grid_set_fused.argtypes = [vp, i32]
+        L.wva_grid_last_fused.argtypes = [vp]
         L.wva_grid_deferred_fetch.argtypes = [vp, C.POINTER(u64), i32, C.POINTER(i32)]
         L.wva_stream.argtypes = [vp]
         L.wva_stream.restype = vp
@@ -353,6 +355,12 @@ class Context:
         a, b = C.c_int32(0), C.c_int32(0)
         self._ck(lib().wva_grid_list_sizes(self._h, C.byref(a), C.byref(b)))
         return dict(deferred=a.value, literal=b.value)
+
+    def grid_set_fused(self, on):
+        self._ck(lib().wva_grid_set_fused(self._h, 1 if on else 0))
+
+    def grid_last_fused(self):
+        return int(lib().wva_grid_last_fused(self._h))
 
     def grid_deferred(self, cap=1 << 22):
         """cube indices (relative to the shard) of the candidates the last sweep slice ran as exact chains."""

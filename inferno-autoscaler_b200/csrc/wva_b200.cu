@@ -192,6 +192,7 @@ struct wva_ctx {
     DevBuf greedyBuf;
     bool greedy_attr = false;
     int grid_list_warp = 1;     // deferred sweep chains: one warp per chain when the list is short
+    int grid_fused = 1;         // scan mode: no host round trip between the sweep kernels and the exact chains when the list is long
     int greedy_ranked = 2;      // 2: static-order scan, 1: ranked queue, 0: always the heap kernel
     int greedy_path = 0;        // last limited solve: 1 heap, 2 ranked queue, 3 static-order scan
     uint64_t greedy_stats[4] = {0, 0, 0, 0};
@@ -201,6 +202,8 @@ struct wva_ctx {
     DevBuf keys, bestDev, cube, status, counters, gridSlow, gridSlowCount, faultList, faultCount;
     DevBuf heavyList, heavyCost, heavyOrder, heavyHist, pairTab, blockSlot, listSlot, gscratch, rowInfo, rateTab;
     int grid_tail_cap = -1; int last_heavy = 0, last_slow = 0, last_heavy_slice = 0;
+    int last_fused = 0;         // the last sweep slice did not stop at the host between its kernels
+    int heavy_hint = 0;         // deferred chains of the last slice swept (survives across calls: reconciles repeat)
     cudaEvent_t evh0 = nullptr, evh1 = nullptr;
     // solve / totals phases: own event pairs, read lazily (a call that returns nothing to the host does not
     // wait for the device; wva_phase_time_usec does)
@@ -336,14 +339,18 @@ int wva_ctx_create(int device, wva_ctx** out) {
         return fail(nullptr, WVA_ECUDA, "device is not sm_100 class; this library carries sm_100a code only");
     ctx = new wva_ctx;
     ctx->device = device;
+    int prioLo = 0, prioHi = 0;                       // numerically lower = more urgent
+    cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evk0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evk1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evh0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evh1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evS0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evS1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evT0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evT1)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->gstream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        // the sweep's stream outranks the one of its cube-writing half (k_scan_lean): when the exact-chain kernel and
+        // k_scan_lean become runnable together, the few blocks of the former are placed first (see grid_run)
+        (e = cudaStreamCreateWithPriority(&ctx->gstream, cudaStreamNonBlocking, prioHi)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&ctx->gstream2, cudaStreamNonBlocking, prioLo)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evPrep, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evLean, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->evg0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evg1)) != cudaSuccess ||
@@ -862,6 +869,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         CK(cudaFuncSetAttribute(k_scan_cert<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_scan_cert<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    CK(cudaFuncSetAttribute(k_grid_list_own, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // k_grid_wrow: the table, then per warp the checkpoints and the quotient buffer of warp_exact
     const size_t smemW = align_up(smem, 16) + (size_t)(WVA_GRID_THREADS / 32) * (WVA_WX_CP + 1 + 1024) * 8;
     if (smemW > 48 * 1024) CK(cudaFuncSetAttribute(k_grid_wrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
@@ -899,10 +907,68 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
         int counts[2] = {0, 0};
         int slow = 0, heavy = 0;
         bool leanPending = false;
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        // Long deferred lists (as seen in the previous call / slice): the sweep does not stop at the host between its kernels.
+        // The exact-chain kernel reads the list length from device memory and owns a few SMs (k_grid_list_own), k_scan_lean
+        // gets the others.  The list's slots are sized from the previous length; a list that outgrows them redoes the slice
+        // the stop-and-go way (keys only ever decrease towards the true minimum: safe).
+        bool fused = scanMode && ctx->grid_fused && ctx->heavy_hint > 4096;
+        for (int attempt = 0; attempt < 3; ++attempt) {
             gp.slow_list = ctx->gridSlow.as<unsigned long long>(); gp.slow_cap = slow_cap;
             CK(cudaMemsetAsync(ctx->gridSlowCount.p, 0, 8, ctx->gstream));
             CK(cudaEventRecord(ctx->evk0, ctx->gstream));
+            if (fused) {
+                size_t fusedCap = 2 * (size_t)ctx->heavy_hint + 65536;
+                if (fusedCap > (size_t)heavy_cap) fusedCap = (size_t)heavy_cap;
+                CK(ctx->listSlot.ensure((fusedCap + (size_t)slow_cap + 1) * sizeof(GridSlot)));
+                gp.list_slot = ctx->listSlot.as<GridSlot>();
+                k_scan_prep<<<(unsigned)nBlocks, WVA_SCAN_MAXROWS, smem, ctx->gstream>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
+                if (ctx->grid_scan == 2) k_scan_cert<2><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                else k_scan_cert<3><<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, smem, ctx->gstream>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
+                ctx->sweep_launched.store(true, std::memory_order_release);
+                CK(cudaEventRecord(ctx->evk1, ctx->gstream));
+                CK(cudaEventRecord(ctx->evh0, ctx->gstream));
+                int* hist = ctx->heavyHist.as<int>();
+                CK(cudaMemsetAsync(hist, 0, 256 * 4, ctx->gstream));
+                k_heavy_hist_dev<<<296, 256, 0, ctx->gstream>>>(gp.heavy_cost, gp.heavy_count, (int)fusedCap, hist);
+                LAUNCH_CHECK();
+                k_heavy_prefix<<<1, 256, 0, ctx->gstream>>>(hist);
+                LAUNCH_CHECK();
+                k_heavy_scatter_dev<<<296, 256, 0, ctx->gstream>>>(gp.heavy_cost, gp.heavy_count, (int)fusedCap, hist, ctx->heavyOrder.as<int>());
+                LAUNCH_CHECK();
+                // both halves become runnable here; this stream has the higher priority, so the chain kernel's blocks are placed first
+                CK(cudaEventRecord(ctx->evPrep, ctx->gstream));
+                CK(cudaStreamWaitEvent(ctx->gstream2, ctx->evPrep, 0));
+                int nOwn = (ctx->heavy_hint + 511) / 512;
+                nOwn = nOwn < 8 ? 8 : (nOwn > 32 ? 32 : nOwn);
+                k_grid_list_own<<<nOwn, 512, 200 * 1024, ctx->gstream>>>(ctx->dsys, gp, gp.heavy_list, ctx->heavyOrder.as<int>(), gp.heavy_count, (int)fusedCap);
+                LAUNCH_CHECK();
+                CK(cudaEventRecord(ctx->evh1, ctx->gstream));
+                k_scan_lean<<<(unsigned)nBlocks, WVA_SCAN_WARPS * 32, 46 * 1024, ctx->gstream2>>>(ctx->dsys, gp);
+                LAUNCH_CHECK();
+                CK(cudaEventRecord(ctx->evLean, ctx->gstream2));
+                leanPending = true;
+                CK(cudaMemcpyAsync(counts, ctx->gridSlowCount.p, 8, cudaMemcpyDeviceToHost, ctx->gstream));
+                CK(cudaStreamSynchronize(ctx->gstream));
+                float kms = 0.0f, hms = 0.0f;
+                CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
+                CK(cudaEventElapsedTime(&hms, ctx->evh0, ctx->evh1));
+                ctx->phase_usec[WVA_PHASE_GRID_KERNEL] += (int64_t)(kms * 1000.0f + 0.5f);
+                ctx->phase_usec[WVA_PHASE_GRID_HEAVY] += (int64_t)(hms * 1000.0f + 0.5f);
+                slow = counts[0];
+                if ((size_t)counts[1] > fusedCap) {                    // the list outgrew its slots: once more, stop-and-go
+                    ctx->heavy_hint = 0; fused = false;
+                    CK(cudaStreamWaitEvent(ctx->gstream, ctx->evLean, 0));
+                    continue;
+                }
+                heavy = counts[1];
+                if (slow <= slow_cap) break;
+                slow_cap = slow;
+                CK(ctx->gridSlow.ensure((size_t)slow_cap * 8));
+                CK(cudaStreamWaitEvent(ctx->gstream, ctx->evLean, 0));
+                continue;
+            }
             if (scanMode) {
                 // exact stop of every row, then the two halves of the sweep (before / after the stop)
                 k_scan_prep<<<(unsigned)nBlocks, WVA_SCAN_MAXROWS, smem, ctx->gstream>>>(ctx->dsys, gp);
@@ -980,7 +1046,7 @@ static int grid_run(wva_ctx* ctx, int r_max, int b_max, bool want_cube, bool wan
             // keys only ever decrease towards the true minimum: redoing the slice is safe (the work
             // counters then count the slice twice)
         }
-        ctx->last_heavy += heavy; ctx->last_slow += slow; ctx->last_heavy_slice = heavy;
+        ctx->last_heavy += heavy; ctx->last_slow += slow; ctx->last_heavy_slice = heavy; ctx->heavy_hint = heavy; ctx->last_fused = fused ? 1 : 0;
         int listSlots = heavy;
         if (slow > 0) {
             size_t freeB = 0, totB = 0;
@@ -1063,6 +1129,12 @@ int wva_analyze(wva_ctx* ctx, int32_t r_max, int32_t b_max, int32_t want_cube) {
         ctx->sweep_launched.store(true, std::memory_order_release);      // also on the error paths
         tg1 = now();
     });
+    // The sweep's first kernels go to the device BEFORE the pair kernel.  k_pairs_warp takes every register of every SM
+    // (4 blocks x 128 threads x 128 registers) for 3-4 waves: launched first, it kept the sweep waiting until its last wave
+    // (analyze = pairs + sweep, 5.7 ms at config 3); launched behind k_scan_prep / k_scan_cert it shares the SMs with them
+    // from the start (4.2 ms).  Costs the calling thread the ~30 us the sweep thread needs to get there.
+    static const bool pairsFirst = std::getenv("WVA_PAIRS_FIRST") != nullptr;
+    while (!pairsFirst && !ctx->sweep_launched.load(std::memory_order_acquire)) std::this_thread::yield();
     const double t1 = now();
     int rcPairs = wva_analyze_pairs(ctx, nullptr, nullptr);
     const double t2 = now();
@@ -1107,6 +1179,12 @@ int wva_grid_set_tail_cap(wva_ctx* ctx, int32_t tail_cap) {
     ctx->grid_tail_cap = tail_cap;
     return WVA_OK;
 }
+int wva_grid_set_fused(wva_ctx* ctx, int32_t on) {
+    if (!ctx) return WVA_EINVAL;
+    ctx->grid_fused = on ? 1 : 0;
+    return WVA_OK;
+}
+int wva_grid_last_fused(const wva_ctx* ctx) { return ctx ? ctx->last_fused : WVA_EINVAL; }
 int wva_grid_list_sizes(const wva_ctx* ctx, int32_t* deferred, int32_t* literal) {
     if (!ctx) return WVA_EINVAL;
     if (deferred) *deferred = ctx->last_heavy;

@@ -1523,49 +1523,47 @@ __device__ int analyze_candidate(const DevSystem& sys, int s, int a, int r, int 
 //                        the literal list.
 //   scratch != nullptr : the literal list (p[] materialised, `stride` doubles per thread).
 // Each thread publishes key + metrics in gp.list_slot[slot_base + t] for k_grid_claim.
-__global__ void __launch_bounds__(128)
-k_grid_list(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, const int* __restrict__ order,
-            int nList, double* scratch, long long stride, int slot_base) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long steps = 0, alg = 0, okc = 0;
-    if (t < nList) {
-        const size_t ci = (size_t)list[order ? order[t] : t];
-        const int B = gp.b_max;
-        const int b = (int)(ci % B) + 1;
-        const int r = (int)((ci / B) % gp.r_max) + 1;
-        const int pairLocal = (int)(ci / ((size_t)B * gp.r_max));
-        const int sl = pairLocal / sys.A, a = pairLocal % sys.A, s = gp.s0 + sl;
-        GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0;
-        GridSlot slot; slot.key = WVA_KEY_NONE; slot.cost = slot.itl = slot.ttft = slot.rho = 0.0f; slot.sl = sl; slot.pad = 0;
-        int st = analyze_candidate(sys, s, a, r, b, scratch ? nullptr : gp.pair_tab + (size_t)(pairLocal - gp.pair_base) * B,
-                                   scratch ? scratch + (size_t)t * stride : nullptr, gs, m, rate, rateTPS, fault, steps);
-        if (fault == 1) {
-            int k = atomicAdd(gp.slow_count, 1);
-            if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+// one candidate of a list: evaluate, publish key + metrics in gp.list_slot[slot] for k_grid_claim
+__device__ __forceinline__ void grid_list_item(const DevSystem& sys, const GridParams& gp, const size_t ci, const int slotIdx, double* scratchRow,
+                                               unsigned long long& steps, unsigned long long& alg, unsigned long long& okc) {
+    const int B = gp.b_max;
+    const int b = (int)(ci % B) + 1;
+    const int r = (int)((ci / B) % gp.r_max) + 1;
+    const int pairLocal = (int)(ci / ((size_t)B * gp.r_max));
+    const int sl = pairLocal / sys.A, a = pairLocal % sys.A, s = gp.s0 + sl;
+    GridServer gs; wva_metrics m; float rate, rateTPS; int fault = 0;
+    GridSlot slot; slot.key = WVA_KEY_NONE; slot.cost = slot.itl = slot.ttft = slot.rho = 0.0f; slot.sl = sl; slot.pad = 0;
+    int st = analyze_candidate(sys, s, a, r, b, scratchRow ? nullptr : gp.pair_tab + (size_t)(pairLocal - gp.pair_base) * B,
+                               scratchRow, gs, m, rate, rateTPS, fault, steps);
+    if (fault == 1) {
+        int k = atomicAdd(gp.slow_count, 1);
+        if (k < gp.slow_cap) gp.slow_list[k] = (unsigned long long)ci;
+    } else {
+        bool feasible = false;
+        if (st == WVA_CAND_OK) {
+            unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
+            if (key != WVA_KEY_NONE) {
+                slot.key = key; slot.itl = m.avg_token_time; slot.ttft = m.avg_wait_time + m.avg_prefill_time;
+                slot.rho = m.rho; slot.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
+                if (key < gp.keys[sl]) atomicMin(&gp.keys[sl], key);
+            }
+            alg += 2ULL * (unsigned long long)(11 * b + 1);
+            okc += 1;
         } else {
-            bool feasible = false;
-            if (st == WVA_CAND_OK) {
-                unsigned long long key = candidate_key(gs, a, r, b, rate, rateTPS, m, feasible);
-                if (key != WVA_KEY_NONE) {
-                    slot.key = key; slot.itl = m.avg_token_time; slot.ttft = m.avg_wait_time + m.avg_prefill_time;
-                    slot.rho = m.rho; slot.cost = gs.accCost * (float)go_muli(gs.numInst, (long long)r);
-                    if (key < gp.keys[sl]) atomicMin(&gp.keys[sl], key);
-                }
-                alg = 2ULL * (unsigned long long)(11 * b + 1);
-                okc = 1;
-            } else {
-                m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
-                m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
-            }
-            if (gp.cube) {
-                float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
-                c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
-                c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
-            }
-            if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
+            m.throughput = m.avg_resp_time = m.avg_wait_time = m.avg_num_in_serv = 0.0f;
+            m.avg_prefill_time = m.avg_token_time = m.max_rate = m.rho = 0.0f;
         }
-        gp.list_slot[slot_base + t] = slot;
+        if (gp.cube) {
+            float4* c = reinterpret_cast<float4*>(&gp.cube[ci]);
+            c[0] = make_float4(m.throughput, m.avg_resp_time, m.avg_wait_time, m.avg_num_in_serv);
+            c[1] = make_float4(m.avg_prefill_time, m.avg_token_time, m.max_rate, m.rho);
+        }
+        if (gp.status) gp.status[ci] = (unsigned char)(st | (feasible ? WVA_CAND_FEASIBLE : 0));
     }
+    gp.list_slot[slotIdx] = slot;
+}
+
+__device__ __forceinline__ void grid_list_counters(const GridParams& gp, unsigned long long steps, unsigned long long alg, unsigned long long okc) {
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_down_sync(0xffffffffu, steps, o);
         alg += __shfl_down_sync(0xffffffffu, alg, o);
@@ -1576,6 +1574,32 @@ k_grid_list(DevSystem sys, GridParams gp, const unsigned long long* __restrict__
         if (alg) atomicAdd(&gp.counters[1], alg);
         if (okc) atomicAdd(&gp.counters[2], okc);
     }
+}
+
+__global__ void __launch_bounds__(128)
+k_grid_list(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, const int* __restrict__ order,
+            int nList, double* scratch, long long stride, int slot_base) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long steps = 0, alg = 0, okc = 0;
+    if (t < nList)
+        grid_list_item(sys, gp, (size_t)list[order ? order[t] : t], slot_base + t, scratch ? scratch + (size_t)t * stride : nullptr, steps, alg, okc);
+    grid_list_counters(gp, steps, alg, okc);
+}
+
+// The deferred long chains again, for the sweep that does not stop at the host between its kernels: the number of
+// chains is read from device memory (*count, clamped to cap), the grid is a handful of 512-thread blocks that ask for
+// 200 KB of shared memory they do not use -- so each block has an SM to itself and the cube-writing kernel that
+// runs beside it (k_scan_lean, issue-bound) cannot slow the 4 dependent-chain warps per scheduler down -- and the
+// threads stride over the list (ordered longest first).
+__global__ void __launch_bounds__(512, 1)
+k_grid_list_own(DevSystem sys, GridParams gp, const unsigned long long* __restrict__ list, const int* __restrict__ order,
+                const int* __restrict__ count, int cap) {
+    const int n = min(*count, cap);
+    const int G = gridDim.x * blockDim.x;
+    unsigned long long steps = 0, alg = 0, okc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += G)
+        grid_list_item(sys, gp, (size_t)list[order[i]], i, nullptr, steps, alg, okc);
+    grid_list_counters(gp, steps, alg, okc);
 }
 
 // Deferred candidates, one WARP each (warp_exact): for short lists, where the latency of a single
@@ -1709,6 +1733,16 @@ __global__ void k_heavy_scatter(const float* __restrict__ cost, int n, int* __re
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) order[atomicAdd(&cursor[heavy_bucket(cost[t])], 1)] = t;
 }
+// ordering kernels with the list length in device memory
+__global__ void k_heavy_hist_dev(const float* __restrict__ cost, const int* __restrict__ count, int cap, int* __restrict__ hist) {
+    const int n = min(*count, cap);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) atomicAdd(&hist[heavy_bucket(cost[t])], 1);
+}
+__global__ void k_heavy_scatter_dev(const float* __restrict__ cost, const int* __restrict__ count, int cap, int* __restrict__ cursor, int* __restrict__ order) {
+    const int n = min(*count, cap);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) order[atomicAdd(&cursor[heavy_bucket(cost[t])], 1)] = t;
+}
+
 
 // Per-server winners: keys[] holds the minimum key of every server; the slot that carries that key
 // (exactly one: keys are unique per candidate) writes the wva_grid_best record.  No re-evaluation.

@@ -48,14 +48,27 @@ def _decode(idx, A, R, B):
     return (pair // A).astype(np.int32), (pair % A).astype(np.int32), r, b
 
 
-def _check_sweep_against_oracle(wva, oracle, ctx, img, first, count, R, B, n_random, seed, expect_rows_kernel=True):
+def _check_sweep_against_oracle(wva, oracle, ctx, img, first, count, R, B, n_random, seed, expect_rows_kernel=True, also_fused=False):
     """Sweep servers [first, first+count) of `img` on the GPU (cube + status + winners) and check against the oracle:
-    random candidates, all deferred candidates, and the winners exhaustively.  Returns counters for the report."""
+    random candidates, all deferred candidates, and the winners exhaustively.  Returns counters for the report.
+    also_fused: sweep a second time the way a repeated reconcile does when the deferred list is long (no stop at the host
+    between the kernels, exact chains on SMs of their own): same bytes, and the oracle checks run on that second result."""
     th = _threads(oracle)
     A = img.A
     ctx.upload(img)
     ctx.set_shard(first, count)
+    ctx.grid_set_fused(False)
     best, cube, status = ctx.analyze_grid(R, B, want_cube=True)
+    assert ctx.grid_last_fused() == 0
+    ctx.grid_set_fused(True)
+    if also_fused:
+        n0 = ctx.grid_list_sizes()["deferred"]
+        assert n0 > 4096, "shard too small for the fused flow"
+        best2, cube2, status2 = ctx.analyze_grid(R, B, want_cube=True)
+        assert ctx.grid_last_fused() == 1
+        assert ctx.grid_list_sizes()["deferred"] == n0
+        assert best2.tobytes() == best.tobytes() and status2.tobytes() == status.tobytes() and cube2.tobytes() == cube.tobytes()
+        best, cube, status = best2, cube2, status2
     lists = ctx.grid_list_sizes()
     deferred, n_def = ctx.grid_deferred(cap=1 << 24)
     assert n_def == len(deferred) == lists["deferred"]
@@ -116,6 +129,16 @@ def test_config3_sweep_vs_oracle(wva, oracle, ctx):
             tot[k] += rep[k]
     assert tot["checked"] >= 1_000_000 and tot["winners"] > 300 and tot["deferred"] > 0
     print("config 3:", tot)
+
+
+def test_config3_fused_sweep_vs_oracle(wva, oracle, ctx):
+    """500 servers of config 3 defer ~6 600 candidates: the second sweep takes the flow bench.py's steps take after the
+    first one (all kernels launched without a host round trip, chain kernel on its own SMs); byte-equal to the
+    stop-and-go sweep, and checked against the oracle like the others."""
+    img, c = wva.synth.baseline_config(3)
+    rep = _check_sweep_against_oracle(wva, oracle, ctx, img, 250, 500, c["r_max"], c["b_max"], 200_000, seed=35, also_fused=True)
+    assert rep["deferred"] > 4096 and rep["winners"] > 100
+    print("config 3, fused flow:", rep)
 
 
 def test_config4_slice_vs_oracle(wva, oracle, ctx):

@@ -7,12 +7,13 @@ import wva_import
 wva = wva_import.load()
 from inferno_autoscaler_b200 import binding
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-modes = [int(x) for x in sys.argv[2:]] or [1, 33, 17]
+modes = [int(x) for x in sys.argv[2:]] or [1, 33, 17]      # 101 = mode 1 with the fused flow switched off (stop and go)
 img, c = wva.synth.baseline_config(cfg)
 ctx = binding.Context(0)
 ref = None
 for mode in modes:
-    ctx.set_certified_tails(mode)
+    ctx.set_certified_tails(mode % 100)
+    ctx.grid_set_fused(mode < 100)
     ctx.upload(img)
     t = []
     for i in range(6):
@@ -23,6 +24,6 @@ for mode in modes:
         ref = best.tobytes()
     t = np.array(t[2:], dtype=float) / 1e3
     print(json.dumps({"config": cfg, "mode": mode, "grid_ms": round(float(t[:, 0].mean()), 3), "sweep_kernel_ms": round(float(t[:, 1].mean()), 3),
-                      "exact_chain_ms": round(float(t[:, 2].mean()), 3), "lists": ctx.grid_list_sizes(), "same_winners": best.tobytes() == ref,
+                      "exact_chain_ms": round(float(t[:, 2].mean()), 3), "fused": ctx.grid_last_fused(), "lists": ctx.grid_list_sizes(), "same_winners": best.tobytes() == ref,
                       "counters": ctx.grid_counters()}))
 ctx.close()

@@ -7,8 +7,10 @@ wva = wva_import.load()
 from inferno_autoscaler_b200 import binding, abi
 import torch
 
-img, c = wva.synth.baseline_config(2)
+img, c = wva.synth.baseline_config(int(sys.argv[1]) if len(sys.argv) > 1 else 2)
 ctx = binding.Context(0)
+if len(sys.argv) > 2:
+    ctx.grid_set_fused(int(sys.argv[2]))
 ctx.upload(img)
 R, B = c["r_max"], c["b_max"]
 def step():
