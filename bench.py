@@ -74,7 +74,7 @@ def ncu_summary(kernels, cfg_id):
     try:
         tot, tsum, psum, seen = 0.0, 0.0, 0.0, set()
         for k in json.load(open(p)):
-            name = k["kernel"].split("(")[0].split("::")[-1]
+            name = k["kernel"].split("(")[0].split("::")[-1].replace("void ", "").split("<")[0].strip()
             if name in kernels and name not in seen:
                 seen.add(name)
                 for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -431,7 +431,7 @@ def main():
         # the sweep = k_scan_prep (exact stop per row) + k_scan_cert (before the stop) + k_scan_lean (after it) with the
         # exact-chain kernels for uncertified candidates overlapped on a second stream: timed as one phase (CUDA events
         # around the whole sweep on the sweep's stream)
-        k_names = ["k_scan_prep", "k_scan_cert", "k_scan_lean", "k_grid_list", "k_grid_list_warp"]
+        k_names = ["k_scan_prep", "k_scan_cert", "k_scan_lean", "k_grid_list", "k_grid_list_own", "k_grid_list_warp"]
         k_us = float(np.mean(phase_us["grid"]))
         bytes_per_cand = 33.0 if want_cube else 0.0               # 32 B AnalysisMetrics + 1 status byte when the cube is materialised
         alg_bytes = bytes_per_cand * cand_rank + 88.0 * per_rank * img.A + 32.0 * per_rank

@@ -32,4 +32,4 @@ def test_profiles_readme_lists_existing_files():
     # and nothing measured sits there undocumented
     for f in present - {"README.md"}:
         stem = f.rsplit(".", 1)[0]
-        assert f in readme or stem in readme or any(stem.startswith(p) for p in ("bench_r01_n",)), f
+        assert f in readme or stem in readme or any(stem.startswith(p) for p in ("bench_r01_n", "bench_r02_multi_")), f
