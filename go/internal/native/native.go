@@ -179,6 +179,24 @@ func (c *Context) Analyze(rMax, bMax int) error {
 	return c.err(C.wva_analyze(c.ctx, C.int32_t(rMax), C.int32_t(bMax), 0), "wva_analyze")
 }
 
+// Tuning knobs (results never depend on them; see include/wva_b200.h).  SolvePath: 2 = static-order scan (default),
+// 1 = ranked queue, 0 = heap.  SweepFused: false = the sweep always stops at the host between its kernels.
+func (c *Context) SetSolvePath(path int) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return c.err(C.wva_solve_set_ranked(c.ctx, C.int32_t(path)), "wva_solve_set_ranked")
+}
+
+func (c *Context) SetSweepFused(on bool) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	v := C.int32_t(0)
+	if on {
+		v = 1
+	}
+	return c.err(C.wva_grid_set_fused(c.ctx, v), "wva_grid_set_fused")
+}
+
 // SetShard restricts the following calls to servers [first, first+count) (one process per GPU).
 func (c *Context) SetShard(first, count int) error {
 	c.mu.Lock()
