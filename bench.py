@@ -208,11 +208,20 @@ def run_reference(args, rank, world):
     R, B = c["r_max"], c["b_max"]
     threads = oracle.hardware_threads()
     sub, n_srv = cpu_sample(args, img, wva, oracle)
-    cand = n_srv * img.A * R * B
 
     def step():
         cpu_reference_step(oracle, sub, R, B, threads, args.limited, wva.abi)
 
+    # the whole --steps K --warmup W run has to end within a few minutes on whatever host this is: time one step of the
+    # asked-for sample and shrink the sample (never below 2 servers) if K + W of them would take more than ~150 s
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    budget = 150.0
+    if t1 * (args.steps + args.warmup) > budget and n_srv > 2:
+        args.ref_servers = max(2, int(n_srv * budget / (t1 * (args.steps + args.warmup))))
+        sub, n_srv = cpu_sample(args, img, wva, oracle)
+    cand = n_srv * img.A * R * B
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
