@@ -22,3 +22,14 @@ def test_static_order_all_keys_tie():
         servers = [(1, [(0, rng.randrange(2), rng.randint(1, 5), False) for _ in range(rng.randint(1, 4))]) for _ in range(S)]
         avail = [rng.randint(0, 30), rng.randint(0, 30)]
         assert gm.queue_allocate(servers, avail) == gm.static_allocate(servers, avail)
+
+
+def test_batch_resolution_equals_one_by_one():
+    """the warp's lane-parallel resolution of 32 events (register copy of the type's capacity, successes applied in lane
+    order) against processing them one by one; counts may be negative (Go's wrapped product) so capacities may grow"""
+    rng = random.Random(13)
+    for r in range(6000):
+        ev, avail, done = gm.random_batch(rng)
+        a1, d1 = list(avail), set(done)
+        a2, d2 = list(avail), set(done)
+        assert (gm.batch_resolve(ev, a1, d1), a1, d1) == (gm.sequential_resolve(ev, a2, d2), a2, d2), (ev, avail, done)

@@ -157,6 +157,78 @@ def static_allocate(servers, avail):
     return placed, unalloc, avail
 
 
+def batch_resolve(events, avail, done):
+    """greedy_scan_batch: up to 32 events in lane order, resolved the way the warp does it.  events: list of
+    (server, type, count, skip, last); returns (placed [(server, lane)], unalloc [server...]); avail / done are updated.
+    Every lane tests against a register copy of its type's capacity; the first lane that can stop (placement or drop)
+    does; lanes of that type re-test, later lanes of that server die; repeat.  Equals one-by-one processing also when a
+    negative count makes the capacity grow."""
+    n = len(events)
+    alive = [e[0] not in done for e in events]
+    av = [avail[e[1]] for e in events]
+    cand = [alive[i] and (events[i][3] or av[i] >= events[i][2]) for i in range(n)]
+    won = [False] * n
+    while any(cand):
+        f = cand.index(True)
+        sf, tf, cf, skf, _ = events[f]
+        won[f] = True; cand[f] = False; alive[f] = False
+        for i in range(n):
+            s, t, c, sk, _ = events[i]
+            if not skf and not sk and t == tf:
+                av[i] -= cf
+                if i > f and alive[i]:
+                    cand[i] = av[i] >= c
+            if i > f and alive[i] and s == sf:
+                alive[i] = False; cand[i] = False
+    placed, unalloc = [], []
+    for i in range(n):
+        s, t, c, sk, last = events[i]
+        if won[i]:
+            if not sk:
+                avail[t] -= c
+                placed.append((s, i))
+            done.add(s)
+        elif alive[i] and last:
+            unalloc.append(s)
+            done.add(s)
+    return placed, unalloc
+
+
+def sequential_resolve(events, avail, done):
+    placed, unalloc = [], []
+    for i, (s, t, c, sk, last) in enumerate(events):
+        if s in done:
+            continue
+        if sk:
+            done.add(s)
+        elif avail[t] >= c:
+            avail[t] -= c
+            placed.append((s, i))
+            done.add(s)
+        elif last:
+            unalloc.append(s)
+            done.add(s)
+    return placed, unalloc
+
+
+def random_batch(rng):
+    """up to 32 events as a batch of the pass holds them: a server's candidates in their own order (the last one flagged),
+    interleaved with other servers'; some servers have stopped before the batch"""
+    T = rng.randint(1, 3)
+    seqs = []
+    for s in range(rng.randint(1, 10)):
+        nc = rng.randint(1, 5)
+        first = rng.randint(0, nc - 1)                       # the batch may start in the middle of a server's candidates
+        seqs.append([(s, rng.randrange(T), rng.randint(-3, 9), rng.random() < 0.05, k == nc - 1) for k in range(first, nc)])
+    ev = []
+    while any(seqs) and len(ev) < 32:
+        q = rng.choice([x for x in seqs if x])
+        ev.append(q.pop(0))
+    avail = [rng.randint(-2, 20) for _ in range(T)]
+    done = set(rng.sample(range(10), rng.randint(0, 3)))
+    return ev, avail, done
+
+
 def random_case(rng):
     S = rng.randint(1, 40)
     T = rng.randint(1, 3)
@@ -185,6 +257,13 @@ def main():
             print(servers, avail)
             print("queue ", a)
             print("static", b)
+            return 1
+    for r in range(rounds):
+        ev, avail, done = random_batch(rng)
+        a1, d1 = list(avail), set(done)
+        a2, d2 = list(avail), set(done)
+        if (batch_resolve(ev, a1, d1), a1, d1) != (sequential_resolve(ev, a2, d2), a2, d2):
+            print("BATCH MISMATCH", ev, avail, done)
             return 1
     print("ok:", rounds, "cases")
     return 0
