@@ -33,3 +33,12 @@ def test_batch_resolution_equals_one_by_one():
         a1, d1 = list(avail), set(done)
         a2, d2 = list(avail), set(done)
         assert (gm.batch_resolve(ev, a1, d1), a1, d1) == (gm.sequential_resolve(ev, a2, d2), a2, d2), (ev, avail, done)
+
+
+def test_allocate_maximally_batched_equals_sequential():
+    """greedy_allocate_maximally serves 32 servers per step (lane = server, forward-only cursor): same takes as
+    greedy.go:194-223 one server after the other"""
+    rng = random.Random(14)
+    for r in range(4000):
+        servers, avail = gm.random_maximally(rng)
+        assert gm.maximally_sequential(servers, avail) == gm.maximally_batched(servers, avail), (servers, avail)

@@ -271,3 +271,66 @@ def main():
 
 if __name__ == "__main__":
     sys.exit(main())
+
+
+# ---- allocateMaximally (greedy.go:194-223), 32 servers at a time ---------------------------------------------------
+
+def go_div(a, b):
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+def maximally_sequential(servers, avail):
+    """servers: list of candidate lists [(type or -1, upr, cur)]; returns {server: (k, replicas)}"""
+    avail = list(avail)
+    got = {}
+    for s, cands in enumerate(servers):
+        for k, (t, upr, cur) in enumerate(cands):
+            if t < 0 or upr <= 0:
+                continue
+            m = min(go_div(avail[t], upr), cur)
+            if m > 0:
+                got[s] = (k, m)
+                avail[t] -= m * upr
+                break
+    return got, avail
+
+
+def maximally_batched(servers, avail):
+    """greedy_allocate_maximally: lane = server with a forward-only cursor, winners served in list order, the lanes
+    waiting on the served type look again (same candidate first)"""
+    avail = list(avail)
+    got = {}
+    for i0 in range(0, len(servers), 32):
+        lanes = list(range(i0, min(i0 + 32, len(servers))))
+        cur_k = {s: 0 for s in lanes}
+
+        def look(s):
+            cands = servers[s]
+            while cur_k[s] < len(cands):
+                t, upr, cur = cands[cur_k[s]]
+                if t >= 0 and upr > 0 and min(go_div(avail[t], upr), cur) > 0:
+                    return True
+                cur_k[s] += 1
+            return False
+
+        has = {s: look(s) for s in lanes}
+        while any(has.values()):
+            f = min(s for s in lanes if has[s])
+            t, upr, cur = servers[f][cur_k[f]]
+            m = min(go_div(avail[t], upr), cur)
+            got[f] = (cur_k[f], m)
+            avail[t] -= m * upr
+            has[f] = False
+            for s in lanes:
+                if has[s] and servers[s][cur_k[s]][0] == t:
+                    has[s] = look(s)
+    return got, avail
+
+
+def random_maximally(rng):
+    T = rng.randint(1, 3)
+    servers = []
+    for s in range(rng.randint(1, 70)):
+        servers.append([(rng.choice([-1] + list(range(T))), rng.randint(0, 4), rng.randint(0, 6)) for _ in range(rng.randint(0, 5))])
+    return servers, [rng.randint(-3, 40) for _ in range(T)]
