@@ -42,3 +42,10 @@ def test_allocate_maximally_batched_equals_sequential():
     for r in range(4000):
         servers, avail = gm.random_maximally(rng)
         assert gm.maximally_sequential(servers, avail) == gm.maximally_batched(servers, avail), (servers, avail)
+
+
+def test_allocate_equally_round1_batched_equals_sequential():
+    rng = random.Random(15)
+    for r in range(4000):
+        servers, avail = gm.random_maximally(rng)
+        assert gm.equally_round1_sequential(servers, avail) == gm.equally_round1_batched(servers, avail), (servers, avail)

@@ -334,3 +334,56 @@ def random_maximally(rng):
     for s in range(rng.randint(1, 70)):
         servers.append([(rng.choice([-1] + list(range(T))), rng.randint(0, 4), rng.randint(0, 6)) for _ in range(rng.randint(0, 5))])
     return servers, [rng.randint(-3, 40) for _ in range(T)]
+
+
+# ---- allocateEqually, round 1 (greedy.go:239-273): every ticket takes its first replica -------------------------------
+
+def equally_round1_sequential(servers, avail):
+    avail = list(avail)
+    tickets, live = {}, []
+    for s, cands in enumerate(servers):
+        for k, (t, upr, cur) in enumerate(cands):
+            if t >= 0 and upr > 0 and avail[t] >= upr:
+                got = 0
+                if cur > 0:
+                    got = 1
+                    avail[t] -= upr
+                    live.append(s)
+                tickets[s] = (k, got)
+                break
+    return tickets, live, avail
+
+
+def equally_round1_batched(servers, avail):
+    avail = list(avail)
+    tickets, live = {}, []
+    for i0 in range(0, len(servers), 32):
+        lanes = list(range(i0, min(i0 + 32, len(servers))))
+        cur_k = {s: 0 for s in lanes}
+
+        def look(s):
+            cands = servers[s]
+            while cur_k[s] < len(cands):
+                t, upr, cur = cands[cur_k[s]]
+                if t >= 0 and upr > 0 and avail[t] >= upr:
+                    return True
+                cur_k[s] += 1
+            return False
+
+        has = {s: look(s) for s in lanes}
+        batch_live = []
+        while any(has.values()):
+            f = min(s for s in lanes if has[s])
+            t, upr, cur = servers[f][cur_k[f]]
+            got = 0
+            if cur > 0:
+                got = 1
+                avail[t] -= upr
+                batch_live.append(f)
+            tickets[f] = (cur_k[f], got)
+            has[f] = False
+            for s in lanes:
+                if has[s] and servers[s][cur_k[s]][0] == t:
+                    has[s] = look(s)
+        live += batch_live
+    return tickets, live, avail
